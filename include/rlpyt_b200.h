@@ -1,0 +1,85 @@
+/*
+ * rlpyt_b200.h - C ABI of librlpyt_b200.so: the B200 (sm_100a) kernels behind rlpyt's
+ * data-parallel inner loop.
+ *
+ * rlpyt has no FFI layer: its "plugin API" is a set of duck-typed Python classes handed
+ * to the runner (rlpyt/runners/minibatch_rl.py:33-46).  Every entry point below replaces
+ * the ARITHMETIC of one reference function / method (cited per function, paths relative
+ * to the reference checkout); the Python classes in rlpyt_b200/ keep the reference
+ * signatures and call these through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions (all functions):
+ *   - plain C: raw DEVICE pointers + extents + a stream handle (cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  No torch / C++ types cross the boundary.
+ *   - buffers are caller-owned; nothing is allocated or freed behind the caller's back;
+ *     scratch space is passed explicitly (sizes given by rl_*_scratch_bytes helpers).
+ *   - stream-ordered, no host synchronisation inside, re-entrant, no global state other
+ *     than the per-thread last-error string.
+ *   - returns 0 on success, a negative RL_E* code on bad arguments, or a positive
+ *     cudaError_t value if a launch failed.  rl_b200_last_error() returns the text.
+ *   - layouts are the reference's: [T,B] time-major C-contiguous (element (t,b) at
+ *     t*B+b), bool/done as 1 byte 0/1, actions and indices int64.
+ */
+#ifndef RLPYT_B200_H
+#define RLPYT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_OK 0
+#define RL_EINVAL (-1)   /* bad extent / null pointer / unsupported combination */
+#define RL_EALIGN (-2)   /* pointer alignment requirement violated */
+
+/* ABI version (bumped on any signature change) and last error text (thread-local). */
+int rl_b200_abi_version(void);
+const char* rl_b200_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error.  Host-side helper. */
+int rl_b200_sm_count(void);
+
+/* ------------------------------------------------------------------ returns (K1-K4)
+ * algo: 0 = auto, 1 = streaming column kernel (thread per 1/4 columns, sequential in t,
+ *       reference operation order => bit-identical to the reference),
+ *       2 = T-parallel warp-segmented scan (small B; reassociated => <=1e-5 rel).
+ */
+
+/* generalized_advantage_estimation - rlpyt/algos/utils.py:24-40.
+ * advantage[t] = delta_t + (discount*lambda)*nd_t*advantage[t+1], return_ = advantage+value.
+ * gamma_lambda must be (float)((double)discount*(double)gae_lambda) (utils.py:38).
+ * done: [T,B] uint8 (0/1); bootstrap_value: [B]; outputs [T,B]. */
+int rl_gae_f32(const float* reward, const float* value, const uint8_t* done,
+               const float* bootstrap_value, float* advantage, float* return_,
+               int T, int64_t B, float discount, float gamma_lambda, int algo, void* stream);
+
+/* discount_return - rlpyt/algos/utils.py:8-21.  If value!=NULL also writes
+ * advantage = return_ - value (rlpyt/algos/pg/base.py:54-55); else advantage may be NULL. */
+int rl_discount_return_f32(const float* reward, const uint8_t* done,
+                           const float* bootstrap_value, const float* value,
+                           float* return_, float* advantage,
+                           int T, int64_t B, float discount, int algo, void* stream);
+
+/* discount_return_n_step - rlpyt/algos/utils.py:67-101.  reward/done: [T_in,B];
+ * outputs [rlen,B] with rlen = do_truncated ? T_in : T_in-(n_step-1).
+ * discount_pow[k] = (float)pow((double)discount,k), k=0..n_step-1 (host-computed so the
+ * python double pow of utils.py:97 is reproduced), DEVICE pointer. */
+int rl_nstep_return_f32(const float* reward, const uint8_t* done, const float* discount_pow,
+                        float* return_, uint8_t* done_n,
+                        int T_in, int64_t B, int n_step, int do_truncated, void* stream);
+
+/* valid_from_done - rlpyt/algos/utils.py:104-112.  valid: [T,B] float32. */
+int rl_valid_from_done_f32(const uint8_t* done, float* valid, int T, int64_t B, void* stream);
+
+/* Advantage normalisation of process_returns - rlpyt/algos/pg/base.py:65-73:
+ * adv = (adv - mean)/max(std,1e-6), unbiased std, statistics over valid>0 (valid may be
+ * NULL = all).  In place.  scratch: rl_adv_normalize_scratch_bytes(n) bytes, 8B aligned.
+ * stats_out (nullable): 3 floats {mean, std, count} for logging/tests. */
+int64_t rl_adv_normalize_scratch_bytes(int64_t n);
+int rl_adv_normalize_f32(float* advantage, const float* valid, int64_t n,
+                         void* scratch, float* stats_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLPYT_B200_H */

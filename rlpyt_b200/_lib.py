@@ -1,0 +1,96 @@
+"""ctypes binding of librlpyt_b200.so (the C ABI declared in include/rlpyt_b200.h).
+
+The product path has NO CPU fallback: if the library is missing or a call fails, this
+module raises.  Device memory, streams and collectives come from torch (plumbing); the
+arithmetic runs in the hand-written sm_100a kernels behind these entry points.
+"""
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, c_double
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librlpyt_b200.so")
+
+P = c_void_p  # every device / host pointer crosses as void*
+
+# name -> (restype, [argtypes]) ; mirrors include/rlpyt_b200.h one to one.
+SIGNATURES = {
+    "rl_b200_abi_version": (c_int, []),
+    "rl_b200_last_error": (c_char_p, []),
+    "rl_b200_sm_count": (c_int, []),
+    "rl_gae_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_float, c_int, P]),
+    "rl_discount_return_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_int, P]),
+    "rl_nstep_return_f32": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, P]),
+    "rl_valid_from_done_f32": (c_int, [P, P, c_int, c_int64, P]),
+    "rl_adv_normalize_scratch_bytes": (c_int64, [c_int64]),
+    "rl_adv_normalize_f32": (c_int, [P, P, c_int64, P, P, P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it)
+
+
+class B200LibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200LibraryError(
+                f"{LIB_PATH} not found: build it with `python -m rlpyt_b200.csrc.build` "
+                "(or __graft_entry__.build()).  rlpyt_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().rl_b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise B200LibraryError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device (or pinned-host) pointer of a contiguous tensor, or NULL for None."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("rlpyt_b200 kernels need contiguous tensors")
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise B200LibraryError(
+                "rlpyt_b200 kernels run on CUDA tensors only (got a CPU tensor); "
+                "there is no CPU fallback - move the data to the GPU first.")
+
+
+def call(name, *args, n_launch=1):
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    check(rc, name)
+    launch_count += n_launch
