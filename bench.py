@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py - the driver's measurement contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): env-steps/sec of PPO on Atari-shaped data, [T=128, B=256] per GPU, AtariFf
+agent, the reference's PPO hyper-parameters (rlpyt/experiments/configs/atari/pg/atari_ff_ppo.py:5-16);
+plus the GAE-scan GB/s in ``roofline``.
+
+A "step" is one PPO iteration over one [T,B] batch of synthetic samples:
+  value  - ``algo.optimize_agent`` on a batch already resident in HBM (returns + 4x4 minibatch
+           updates: gather, forward, fused loss, backward, all-reduce, clip+Adam);
+  e2e    - the public API loop a user runs: ``sampler.obtain_samples`` (CPU synthetic envs in
+           worker processes, per-step H2D of observations from pinned host memory, agent.step on
+           the GPU, D2H of actions) followed by ``algo.optimize_agent`` (D2H of the OptInfo rows).
+Weak scaling: every rank owns B=256 environments; ``value``/``e2e`` are whole-job aggregates.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_CFG, B_CFG, IMAGE, N_ACTIONS = 128, 256, (4, 84, 84), 6
+PPO_KW = dict(discount=0.99, learning_rate=1e-3, value_loss_coeff=1., entropy_loss_coeff=0.01,
+              clip_grad_norm=1., gae_lambda=0.98, linear_lr_schedule=True, minibatches=4, epochs=4,
+              ratio_clip=0.1)
+ENV_KW = dict(image_shape=IMAGE, n_actions=N_ACTIONS, p_done=1 / 500., p_reward=0.04)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- b200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from rlpyt_b200 import _lib
+    from rlpyt_b200.agents.pg.atari import AtariFfAgent
+    from rlpyt_b200.algos.pg.ppo import PPO
+    from rlpyt_b200.algos import utils as U
+    from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
+    from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cores = len(os.sched_getaffinity(0))
+    n_workers = args.workers or max(1, min(32, cores // world - 2, B_CFG))
+    seed = 0 + 100 * rank                                            # sync_rl.py:82 seeds per rank
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    sampler = GpuSampler(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
+                         max_decorrelation_steps=20)
+    agent = AtariFfAgent()
+    affinity = dict(cuda_idx=local_rank, workers_cpus=[None] * n_workers, set_affinity=False)
+    sampler.initialize(agent, affinity=affinity, seed=seed + 1, bootstrap_value=True, world_size=world, rank=rank)
+    agent.to_device(local_rank)
+    if world > 1:
+        agent.data_parallel()
+    algo = PPO(**PPO_KW)
+    n_itr = 10 ** 6
+    algo.initialize(agent, n_itr, sampler.batch_spec, mid_batch_reset=sampler.mid_batch_reset,
+                    world_size=world, rank=rank)
+    steps_per_itr = T_CFG * B_CFG * world
+    K, W = args.steps, args.warmup
+    itr = 0
+    try:
+        # ---- batch resident in HBM
+        samples, _ = sampler.obtain_samples(itr)
+        agent.train_mode(itr)
+        for _ in range(W):
+            algo.optimize_agent(itr, samples)
+            itr += 1
+        barrier()
+        l0 = _lib.launch_count
+        with ClockSampler(local_rank) as clk_value:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                info = algo.optimize_agent(itr, samples)
+                itr += 1
+            e1.record()
+            barrier()
+        t_value = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        launches = _lib.launch_count - l0
+        value = steps_per_itr * K / t_value
+
+        # ---- end to end through the public API (host buffers, H2D/D2H inside the timed region)
+        for _ in range(W):
+            agent.sample_mode(itr)
+            samples, _ = sampler.obtain_samples(itr)
+            agent.train_mode(itr)
+            algo.optimize_agent(itr, samples)
+            itr += 1
+        barrier()
+        t_sample = 0.0
+        with ClockSampler(local_rank) as clk_e2e:
+            t0 = time.perf_counter()
+            for _ in range(K):
+                agent.sample_mode(itr)
+                ts = time.perf_counter()
+                samples, traj_infos = sampler.obtain_samples(itr)
+                t_sample += time.perf_counter() - ts
+                agent.train_mode(itr)
+                info = algo.optimize_agent(itr, samples)
+                itr += 1
+            barrier()
+            t_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = steps_per_itr * K / t_e2e
+        obs_bytes = int(np.prod(IMAGE))
+        h2d = (T_CFG + 1) * B_CFG * (obs_bytes + 4 + 1) + 16 * (T_CFG * B_CFG // 4) * 8
+        d2h = T_CFG * B_CFG * 8 + 16 * 4 * 4
+    finally:
+        sampler.shutdown()
+
+    out = {
+        "metric": "env-steps/sec PPO Atari [T=128,B=256] at 1/2/4/8 GPU; GAE-scan GB/s",
+        "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_value / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PPO+AtariFfAgent, synthetic Atari env obs (4,84,84) u8, T=128 B=256 per GPU "
+                               "(BASELINE.json configs[2]; configs[4] at N>1), gamma .99 lambda .98 lr 1e-3 clip .1 4x4",
+                   "global_batch": steps_per_itr, "parallelism": f"dp{world}",
+                   "l2": "inputs_larger_than_L2 (925 MB observation batch per rank)",
+                   "env_workers_per_rank": n_workers, "host_cores": cores},
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": t_e2e / K * 1e3, "sampling_ms_per_step_rank0": t_sample / K * 1e3},
+        "gpu_launches": launches,
+        "clocks": clk_value.summary(), "clocks_e2e": clk_e2e.summary(),
+        "last_opt_info": {k: float(np.mean(getattr(info, k))) for k in info._fields},
+    }
+
+    # ---- roofline of the GAE scan kernel at the HBM-bound size, measured live (rank 0)
+    if rank == 0:
+        out["roofline"] = roofline_gae(U)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"], out["gae_ppo_loss"] = cpu_baseline(U)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def roofline_gae(U, T=128, B=1 << 20, reps=10):
+    """Achieved HBM GB/s of the GAE streaming kernel: algorithmic bytes 17 B/element
+    (r4 + v4 + done1 read, adv4 + ret4 written) + 4 B/column bootstrap, CUDA events on the launch
+    stream, inputs (2.3 GB) far larger than L2."""
+    peak, how = peaks()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    r = torch.randn(T, B, device="cuda", generator=gen)
+    v = torch.randn(T, B, device="cuda", generator=gen)
+    d = torch.rand(T, B, device="cuda", generator=gen) < 0.01
+    b = torch.randn(1, B, device="cuda", generator=gen)
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    fn = lambda: U.generalized_advantage_estimation(r, v, d, b, 0.99, 0.98, advantage_dest=adv, return_dest=ret, algo=1)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = float(np.mean(ts))
+    nbytes = T * B * 17 + 4 * B
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["gae_stream_bytes_per_launch"]
+    except Exception:
+        pass
+    return {"kernel": "returns_stream_kernel<4,GAE> [T=128, B=2^20]", "bound": "hbm", "achieved": nbytes / t / 1e9,
+            "peak": peak, "unit": "GB/s", "frac": nbytes / t / 1e9 / peak, "traffic": traffic,
+            "peak_source": how, "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes}
+
+
+def cpu_baseline(U):
+    """The oracle port timed on this box's host cores (rank 0, N=1): (i) one PPO optimize_agent
+    iteration on a bounded [T=128, B=32] sample -> env-steps/s comparable with ``value``;
+    (ii) the north_star unit "reference CPU GAE + PPO-loss" at [128,256] (GAE on torch-CPU tensors +
+    16 x loss fwd+bwd arithmetic at N=8192) next to the same work on the GPU kernels."""
+    from oracle import atari_ff, pg_loss
+    from oracle.ppo import PpoOracle, gae_plus_loss_cpu
+    from rlpyt_b200.algos.pg import loss_ops
+    threads = torch.get_num_threads()
+    rng = np.random.default_rng(0)
+    Tb, Bb = T_CFG, 32
+    obs = rng.integers(0, 256, size=(Tb, Bb) + IMAGE, dtype=np.uint8)
+    action = rng.integers(0, N_ACTIONS, size=(Tb, Bb))
+    reward = rng.choice(np.array([-1, 0, 1], np.float32), size=(Tb, Bb), p=[.02, .96, .02]).astype(np.float32)
+    done = rng.random((Tb, Bb)) < 1 / 500.
+    value = rng.standard_normal((Tb, Bb)).astype(np.float32)
+    prob = rng.dirichlet(np.ones(N_ACTIONS), (Tb, Bb)).astype(np.float32)
+    bv = rng.standard_normal((1, Bb)).astype(np.float32)
+    o = PpoOracle(atari_ff.init_state_dict(IMAGE, N_ACTIONS, 0), n_itr=10 ** 6,
+                  **{k: v for k, v in PPO_KW.items()})
+    o.optimize_agent(0, obs, action, reward, done, value, prob, bv)  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 and time.perf_counter() - t0 < 15:
+        o.optimize_agent(n + 1, obs, action, reward, done, value, prob, bv)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    base = {"value": Tb * Bb / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/ppo.py PpoOracle.optimize_agent, torch-CPU fp32, {threads} threads, "
+                      f"[T={Tb},B={Bb}] batch ({Tb * Bb} of {T_CFG * B_CFG} env-steps/iteration), {n} iterations",
+            "s_per_iteration_sample": dt}
+
+    # (ii) GAE + 16 x PPO-loss, CPU reference arithmetic vs the GPU kernels, full [128,256] size
+    T, B, N, A = T_CFG, B_CFG, 8192, N_ACTIONS
+    r = rng.standard_normal((T, B)).astype(np.float32)
+    v = rng.standard_normal((T, B)).astype(np.float32)
+    d = rng.random((T, B)) < 0.01
+    b = rng.standard_normal((1, B)).astype(np.float32)
+    p_new = rng.dirichlet(np.ones(A), N).astype(np.float32)
+    p_old = rng.dirichlet(np.ones(A), N).astype(np.float32)
+    case = (p_new, rng.standard_normal(N).astype(np.float32), p_old, rng.integers(0, A, N),
+            rng.standard_normal(N).astype(np.float32), rng.standard_normal(N).astype(np.float32), None, 0.1, 1.0, 0.01)
+    gae_plus_loss_cpu(r, v, d, b, 0.99, 0.98, case)
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        gae_plus_loss_cpu(r, v, d, b, 0.99, 0.98, case)
+    cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    rc, vc, dc, bc = cu(r), cu(v), cu(d), cu(b)
+    adv, ret = torch.empty_like(rc), torch.empty_like(rc)
+    pn, vv, po, ac, Rc, Ac = (cu(x) for x in case[:6])
+
+    def gpu_unit():
+        U.generalized_advantage_estimation(rc, vc, dc, bc, 0.99, 0.98, advantage_dest=adv, return_dest=ret)
+        for _ in range(16):
+            p = pn.detach().requires_grad_(True)
+            q = vv.detach().requires_grad_(True)
+            loss, _sc = loss_ops.ppo_loss(p, q, po, ac, Rc, Ac, None, 0.1, 1.0, 0.01)
+            loss.backward()
+    for _ in range(3):
+        gpu_unit()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        gpu_unit()
+    torch.cuda.synchronize()
+    gpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    unit = {"what": "GAE [128,256] + 16 x PPO-loss fwd+bwd (N=8192, A=6), no network", "cpu_ms": cpu_ms,
+            "gpu_ms_wall_incl_python": gpu_ms, "speedup": cpu_ms / gpu_ms, "cpu_threads": threads}
+    return base, unit
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path, as restated by the oracle port (the
+    reference is pure Python and cannot travel to this box): serial CPU rollout + PPO on torch-CPU
+    with all host threads, on a bounded [T=128, B=32] sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import atari_ff
+    from oracle.collector import SerialRollout
+    from oracle.ppo import PpoOracle
+    from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
+    threads = torch.get_num_threads()
+    Tb, Bb = T_CFG, 32
+    np.random.seed(0)
+    torch.manual_seed(0)
+    envs = [SyntheticAtariEnv(**ENV_KW) for _ in range(Bb)]
+    for i, e in enumerate(envs):
+        e.seed(1 + i)
+    sd = atari_ff.init_state_dict(IMAGE, N_ACTIONS, 0)
+    algo = PpoOracle(sd, n_itr=10 ** 6, **PPO_KW)
+    roll = SerialRollout(envs, sd, Tb, N_ACTIONS)
+
+    def step(itr):
+        buf = roll.collect_batch(algo.state_dict())
+        return algo.optimize_agent(itr, buf["observation"], buf["all_action"][1:], buf["all_reward"][1:], buf["done"],
+                                   buf["value"], buf["prob"], buf["bootstrap_value"])
+    K, W = args.steps, args.warmup
+    for i in range(W):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(W + i)
+    dt = time.perf_counter() - t0
+    val = Tb * Bb * K / dt
+    sample = (f"oracle port (collector + PPO, torch-CPU fp32, {threads} threads), bounded sample [T={Tb},B={Bb}] "
+              f"per step ({Tb * Bb} of {T_CFG * B_CFG} env-steps)")
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec PPO Atari [T=128,B=256] at 1/2/4/8 GPU; GAE-scan GB/s",
+        "value": val, "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PPO+AtariFf on CPU (reference algorithm), synthetic Atari env obs (4,84,84) u8", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,53 @@ int64_t rl_adv_normalize_scratch_bytes(int64_t n);
 int rl_adv_normalize_f32(float* advantage, const float* valid, int64_t n,
                          void* scratch, float* stats_out, void* stream);
 
+/* ------------------------------------------------------------------ policy-gradient loss (K5)
+ * Fused forward + gradient of the PPO / A2C loss w.r.t. the network outputs.
+ *   PPO.loss  - rlpyt/algos/pg/ppo.py:136-153, A2C.loss - rlpyt/algos/pg/a2c.py:88-100,
+ *   Categorical.likelihood_ratio/log_likelihood/entropy - rlpyt/distributions/categorical.py:32-43,
+ *   valid_mean - rlpyt/utils/tensor.py:39-46, mean_entropy/mean_perplexity - distributions/base.py:57-68.
+ * prob_*: [N,A] f32 row-major, action: [N] int64, value/return_/advantage: [N] f32,
+ * valid: [N] f32 or NULL (plain mean).  out_scalars: 8 floats
+ *   {loss, entropy, perplexity, pi_loss, value_loss, sum(valid) or N, 0, 0}.
+ * grad_prob [N,A] / grad_value [N] (each nullable) receive dLoss/dprob_new, dLoss/dvalue
+ * for an upstream gradient of 1.  scratch: rl_pg_loss_scratch_bytes(N) bytes, 8B aligned. */
+int64_t rl_pg_loss_scratch_bytes(int64_t N);
+int rl_ppo_loss_f32(const float* prob_new, const float* value, const float* prob_old,
+                    const int64_t* action, const float* return_, const float* advantage,
+                    const float* valid, int64_t N, int A, float ratio_clip,
+                    float value_loss_coeff, float entropy_loss_coeff, float* out_scalars,
+                    float* grad_prob, float* grad_value, void* scratch, void* stream);
+int rl_a2c_loss_f32(const float* prob, const float* value, const int64_t* action,
+                    const float* return_, const float* advantage, const float* valid,
+                    int64_t N, int A, float value_loss_coeff, float entropy_loss_coeff,
+                    float* out_scalars, float* grad_prob, float* grad_value, void* scratch,
+                    void* stream);
+
+/* ------------------------------------------------------------------ indexed row gathers
+ * dst[i,:] = src[idx[i],:], rows of row_bytes bytes, idx int64 in [0, src_rows).
+ * The PPO minibatch former: LossInputs[T_idxs, B_idxs] of rlpyt/algos/pg/ppo.py:94-100 with
+ * idx = T_idx*B + B_idx into the [T*B, ...] view (observations: 28224 B rows), and the plain
+ * "x[T_idxs, B_idxs]" field reads of rlpyt/replays/non_sequence/n_step.py:24-37. */
+int rl_gather_rows(const void* src, const int64_t* idx, void* dst, int64_t n, int64_t row_bytes,
+                   void* stream);
+/* Up to RL_GATHER_MAX_FIELDS small fields (rows multiple of 4 B) with one index vector in one
+ * launch.  src/dst/row_bytes are HOST arrays of n_fields entries (device pointers inside). */
+#define RL_GATHER_MAX_FIELDS 8
+int rl_gather_rows_multi(int n_fields, const void* const* src, void* const* dst,
+                         const int64_t* row_bytes, const int64_t* idx, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ optimizer step
+ * Global-norm clip + Adam on one flat fp32 buffer: torch.nn.utils.clip_grad_norm_ +
+ * torch.optim.Adam.step() as used at rlpyt/algos/pg/ppo.py:101-104 / a2c.py:50-53.
+ * grad_scale multiplies the gradient first (1/world_size after a SUM all-reduce: the DDP
+ * average of rlpyt/agents/base.py:118-136).  max_norm <= 0 disables clipping.  step >= 1 is
+ * the Adam step count AFTER this update.  norm_out (nullable): pre-clip total norm (the
+ * reference's gradNorm).  scratch: rl_clip_adam_scratch_bytes(n) bytes. */
+int64_t rl_clip_adam_scratch_bytes(int64_t n);
+int rl_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                     float max_norm, float grad_scale, float* norm_out, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

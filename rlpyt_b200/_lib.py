@@ -27,6 +27,14 @@ SIGNATURES = {
     "rl_valid_from_done_f32": (c_int, [P, P, c_int, c_int64, P]),
     "rl_adv_normalize_scratch_bytes": (c_int64, [c_int64]),
     "rl_adv_normalize_f32": (c_int, [P, P, c_int64, P, P, P]),
+    "rl_pg_loss_scratch_bytes": (c_int64, [c_int64]),
+    "rl_ppo_loss_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float, c_float, P, P, P, P, P]),
+    "rl_gather_rows": (c_int, [P, P, P, c_int64, c_int64, P]),
+    "rl_gather_rows_multi": (c_int, [c_int, P, P, P, P, c_int64, P]),
+    "rl_clip_adam_scratch_bytes": (c_int64, [c_int64]),
+    "rl_clip_adam_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64,
+                                 c_float, c_float, P, P, P]),
+    "rl_a2c_loss_f32": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_float, c_float, P, P, P, P, P]),
 }
 
 _lock = threading.Lock()

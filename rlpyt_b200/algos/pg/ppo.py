@@ -1,0 +1,120 @@
+"""Proximal Policy Optimisation on device-resident samples (mirror of
+``rlpyt/algos/pg/ppo.py:16-154``: same constructor, ``initialize``, ``optimize_agent``, ``loss``).
+
+Where the time went in the reference and what replaces it:
+* ``process_returns``: T-step Python loop on torch-CPU tensors -> GAE scan kernel;
+* ``loss_inputs[T_idxs, B_idxs]`` (:99-100): a fancy-index per field, observations first copied
+  to the device (:72) -> one 16-byte-vectorised row-gather kernel for the observations
+  (231 MB/minibatch) + one multi-field gather for the scalars, all from the resident [T,B] buffers;
+* loss arithmetic on CPU with D2H of the network outputs -> one fused forward+gradient kernel;
+* DDP all-reduce + clip_grad_norm_ + Adam -> ``FlatAdam.clip_and_step`` (1 NCCL call, 2 kernels);
+* 4 ``.item()`` host syncs per update (:106-109) -> one D2H of all OptInfo rows per iteration.
+"""
+import numpy as np
+import torch
+
+from rlpyt_b200.agents.base import AgentInputs
+from rlpyt_b200.algos.optim import FlatAdam
+from rlpyt_b200.algos.pg import loss_ops
+from rlpyt_b200.algos.pg.base import PolicyGradientAlgo, OptInfo
+from rlpyt_b200.utils.collections import namedarraytuple
+from rlpyt_b200.utils.gather import gather_rows, gather_rows_multi
+from rlpyt_b200.utils.misc import iterate_mb_idxs
+
+LossInputs = namedarraytuple("LossInputs",
+                             ["agent_inputs", "action", "return_", "advantage", "valid", "old_dist_info"])
+
+
+class PPO(PolicyGradientAlgo):
+
+    def __init__(self, discount=0.99, learning_rate=0.001, value_loss_coeff=1., entropy_loss_coeff=0.01,
+                 OptimCls=FlatAdam, optim_kwargs=None, clip_grad_norm=1., initial_optim_state_dict=None,
+                 gae_lambda=1, minibatches=4, epochs=4, ratio_clip=0.1, linear_lr_schedule=True,
+                 normalize_advantage=False):
+        self.discount = discount
+        self.learning_rate = learning_rate
+        self.value_loss_coeff = value_loss_coeff
+        self.entropy_loss_coeff = entropy_loss_coeff
+        self.OptimCls = OptimCls
+        self.optim_kwargs = dict() if optim_kwargs is None else optim_kwargs
+        self.clip_grad_norm = clip_grad_norm
+        self.initial_optim_state_dict = initial_optim_state_dict
+        self.gae_lambda = gae_lambda
+        self.minibatches = minibatches
+        self.epochs = epochs
+        self.ratio_clip = ratio_clip
+        self.linear_lr_schedule = linear_lr_schedule
+        self.normalize_advantage = normalize_advantage
+
+    def initialize(self, *args, **kwargs):
+        """ppo.py:46-57."""
+        super().initialize(*args, **kwargs)
+        self._batch_size = self.batch_spec.size // self.minibatches  # for logging
+        if self.linear_lr_schedule:
+            self.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(
+                optimizer=self.optimizer, lr_lambda=lambda itr: (self.n_itr - itr) / self.n_itr)
+            self._ratio_clip = self.ratio_clip
+
+    def optimize_agent(self, itr, samples):
+        """ppo.py:59-115 (feed-forward agents; the recurrent branch is out of scope)."""
+        if self.agent.recurrent:
+            raise NotImplementedError("recurrent PPO is outside the accelerated path (SURVEY.md section 8f)")
+        dev = self._device()
+        obs = self._on_device(samples.env.observation)               # ppo.py:67-72 (no-op when resident)
+        prev_action = self._on_device(samples.agent.prev_action)
+        prev_reward = self._on_device(samples.env.prev_reward)
+        if hasattr(self.agent, "update_obs_rms"):
+            self.agent.update_obs_rms(obs)
+        return_, advantage, valid = self.process_returns(samples)     # ppo.py:75
+        action = self._on_device(samples.agent.action)
+        old_prob = self._on_device(samples.agent.agent_info.dist_info.prob)
+        T, B = samples.env.reward.shape[:2]
+        batch_size = T * B
+        flat = lambda x: x.reshape((batch_size,) + tuple(x.shape[2:]))
+        obs_f = flat(obs)
+        small = [flat(prev_action), flat(prev_reward), flat(action), flat(return_), flat(advantage), flat(old_prob)]
+        if valid is not None:
+            small.append(flat(valid))
+        mb_size = batch_size // self.minibatches                       # ppo.py:90-91
+        n_updates = self.epochs * (batch_size // mb_size)
+        stats = torch.zeros((n_updates, 4), dtype=torch.float32, device=dev)
+        fused_opt = isinstance(self.optimizer, FlatAdam)
+        u = 0
+        for _ in range(self.epochs):                                   # ppo.py:92
+            for idxs in iterate_mb_idxs(batch_size, mb_size, shuffle=True):   # ppo.py:93
+                rows_np = (idxs % T) * B + (idxs // T)                 # ppo.py:94-95: [T_idxs, B_idxs]
+                rows = torch.from_numpy(rows_np).to(dev, non_blocking=True)
+                self.optimizer.zero_grad()                             # ppo.py:96
+                obs_mb = gather_rows(obs_f, rows)
+                got = gather_rows_multi(small, rows)
+                pa_mb, pr_mb, act_mb, ret_mb, adv_mb, oldp_mb = got[:6]
+                valid_mb = got[6] if valid is not None else None
+                dist_info, value = self.agent(obs_mb, pa_mb, pr_mb)    # ppo.py:133
+                loss, sc = loss_ops.ppo_loss(dist_info.prob, value, oldp_mb, act_mb, ret_mb, adv_mb, valid_mb,
+                                             self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
+                loss.backward()                                        # ppo.py:101
+                if fused_opt:
+                    grad_norm = self.optimizer.clip_and_step(self.clip_grad_norm)
+                else:
+                    grad_norm = torch.nn.utils.clip_grad_norm_(self.agent.parameters(), self.clip_grad_norm)
+                    self.optimizer.step()
+                stats[u, 0] = sc[0]
+                stats[u, 1] = grad_norm.reshape(())
+                stats[u, 2:4] = sc[1:3]
+                u += 1
+                self.update_counter += 1
+        if self.linear_lr_schedule:                                    # ppo.py:110-113
+            self.lr_scheduler.step()
+            self.ratio_clip = self._ratio_clip * (self.n_itr - itr) / self.n_itr
+        host = stats[:u].cpu().numpy().astype(np.float64)              # the iteration's single D2H sync
+        return OptInfo(loss=host[:, 0].tolist(), gradNorm=host[:, 1].tolist(),
+                       entropy=host[:, 2].tolist(), perplexity=host[:, 3].tolist())
+
+    def loss(self, agent_inputs, action, return_, advantage, valid, old_dist_info, init_rnn_state=None):
+        """ppo.py:117-154 signature; returns device 0-dim tensors ``(loss, entropy, perplexity)``."""
+        if init_rnn_state is not None:
+            raise NotImplementedError("recurrent PPO is outside the accelerated path")
+        dist_info, value = self.agent(*agent_inputs)
+        loss, sc = loss_ops.ppo_loss(dist_info.prob, value, old_dist_info.prob, action, return_, advantage,
+                                     valid, self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
+        return loss, sc[1], sc[2]

@@ -1,0 +1,88 @@
+"""Sample-buffer construction (mirror of ``rlpyt/samplers/buffer.py:11-82``) - B200 layout.
+
+The reference keeps the whole ``[T,B]`` batch in OS shared memory, lets the workers fill it, and
+the algorithm later copies 925 MB of observations to the GPU (ppo.py:72).  Here the batch lives in
+HBM from the start:
+
+* device-resident (one allocation each, T-major C-contiguous exactly like buffer.py:28-45):
+  ``all_action[T+1,B]`` (``action = [1:]``, ``prev_action = [:-1]`` alias the same block),
+  ``agent_info[T,B]{prob[A], value}``, ``bootstrap_value[1,B]``, ``observation[T,B,C,H,W]`` u8,
+  ``all_reward[T+1,B]`` (``reward`` / ``prev_reward`` aliases), ``done[T,B]`` bool;
+* host: only the ``[B]`` step-exchange buffer (page-locked, fork-shared with the env workers) and the
+  ``env_info[T,B]`` log fields.  Each step's observations go pinned-host -> ``observation[t]``
+  with one async H2D; nothing is copied a second time.
+"""
+import numpy as np
+import torch
+
+from rlpyt_b200.agents.base import AgentInputs
+from rlpyt_b200.samplers.collections import Samples, AgentSamples, AgentSamplesBsv, EnvSamples
+from rlpyt_b200.utils.buffer import buffer_from_example, torchify_buffer
+from rlpyt_b200.utils.collections import namedarraytuple
+
+StepBuffer = namedarraytuple("StepBuffer", ["observation", "action", "reward", "done"])
+
+
+def get_example_outputs(agent, env):
+    """One env step + one agent step to learn every field's shape/dtype (buffer.py:60-82)."""
+    o = env.reset()
+    a = env.action_space.sample()
+    o, r, d, env_info = env.step(a)
+    r = np.asarray(r, dtype="float32")
+    agent.reset()
+    agent_inputs = torchify_buffer(AgentInputs(np.asarray(o), np.asarray(a), r))
+    a, agent_info = agent.step(*agent_inputs)
+    return dict(observation=np.asarray(o), reward=r, done=np.asarray(d, dtype=bool), env_info=env_info,
+                action=a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a),
+                agent_info=_to_numpy(agent_info))
+
+
+def _to_numpy(buf):
+    if isinstance(buf, torch.Tensor):
+        return buf.detach().cpu().numpy()
+    if isinstance(buf, np.ndarray) or buf is None:
+        return buf
+    return buf._make(tuple(_to_numpy(b) for b in buf))
+
+
+def pin_shared(arr):
+    """Page-lock an existing (fork-shared) numpy array so H2D/D2H copies from it are async DMA.
+    Returns True on success; failure only costs speed."""
+    if not torch.cuda.is_available() or arr.nbytes == 0:
+        return False
+    try:
+        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+        return int(rc) == 0
+    except Exception:
+        return False
+
+
+def build_samples_buffer(agent, env, batch_spec, bootstrap_value=False, device=None, share_host=False,
+                         examples=None):
+    """-> (samples, host, examples).  ``samples``: Samples namedarraytuple of CUDA tensors
+    (``env.env_info`` stays on the host); ``host``: dict with the step-exchange buffer
+    (numpy + torch views), ``env_info`` numpy buffer."""
+    if examples is None:
+        examples = get_example_outputs(agent, env)
+    T, B = batch_spec
+    cu = dict(where="cuda", device=device)
+    all_action = buffer_from_example(examples["action"], (T + 1, B), **cu)
+    agent_info = buffer_from_example(examples["agent_info"], (T, B), **cu)
+    agent_buf = AgentSamples(action=all_action[1:], prev_action=all_action[:-1], agent_info=agent_info)
+    if bootstrap_value:
+        bv = buffer_from_example(examples["agent_info"].value, (1, B), **cu)
+        agent_buf = AgentSamplesBsv(*agent_buf, bootstrap_value=bv)
+    observation = buffer_from_example(examples["observation"], (T, B), **cu)
+    all_reward = buffer_from_example(examples["reward"], (T + 1, B), **cu)
+    done = buffer_from_example(examples["done"], (T, B), **cu)
+    env_info_np = buffer_from_example(examples["env_info"], (T, B), share_memory=share_host)
+    env_buf = EnvSamples(observation=observation, reward=all_reward[1:], prev_reward=all_reward[:-1],
+                         done=done, env_info=torchify_buffer(env_info_np))
+    samples = Samples(agent=agent_buf, env=env_buf)
+
+    step_np = StepBuffer(*(buffer_from_example(examples[k], B, share_memory=share_host)
+                           for k in ("observation", "action", "reward", "done")))
+    pinned = all(pin_shared(a) for a in step_np)
+    host = dict(step_np=step_np, step_pyt=torchify_buffer(step_np), env_info_np=env_info_np, pinned=pinned,
+                all_action=all_action, all_reward=all_reward)
+    return samples, host, examples

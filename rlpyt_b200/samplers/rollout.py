@@ -1,0 +1,83 @@
+"""Master-side step engine shared by the serial and the parallel GPU sampler: moves one step of
+observations pinned-host -> HBM, runs ``agent.step`` on the resident slices, records the
+outputs in the ``[T,B]`` device buffers and hands the actions back to the env side.
+
+This is the device half of ``ActionServer.serve_actions`` (rlpyt/samplers/parallel/gpu/
+action_server.py:17-74) and of ``CpuResetCollector.collect_batch`` (rlpyt/samplers/parallel/cpu/
+collectors.py:25-65); the env half stays on the CPU.
+"""
+import numpy as np
+import torch
+
+
+class DeviceRollout:
+
+    def __init__(self, samples, host, agent, device):
+        self.samples, self.host, self.agent = samples, host, agent
+        self.device = device
+        self.step_np, self.step_pyt = host["step_np"], host["step_pyt"]
+        self.all_action, self.all_reward = host["all_action"], host["all_reward"]
+        B = self.step_np.action.shape[0]
+        self.B = B
+        self.T = samples.env.done.shape[0]
+        # agent inputs of the current step (prev_action / prev_reward), resident
+        self.in_action = torch.zeros_like(self.all_action[0])
+        self.in_reward = torch.zeros_like(self.all_reward[0])
+        self.obs_extra = torch.zeros_like(samples.env.observation[0])  # final obs (bootstrap)
+        self.done_step = torch.zeros(B, dtype=torch.bool, device=device)
+        self.stream = torch.cuda.current_stream(device)
+
+    # ---- H2D of what the envs produced since the last step ---------------------------------------
+    def upload(self, k, zero_inputs_on_done):
+        """Event k (0..T): the envs have written observation(k), reward(k-1), done(k-1) into the
+        step buffer.  Record them at their [T,B] rows and stage the agent inputs."""
+        s = self.samples
+        obs_dst = s.env.observation[k] if k < self.T else self.obs_extra
+        obs_dst.copy_(self.step_pyt.observation, non_blocking=True)
+        self.all_reward[k].copy_(self.step_pyt.reward, non_blocking=True)       # reward(k-1) = prev_reward(k)
+        self.done_step.copy_(self.step_pyt.done, non_blocking=True)
+        if k >= 1:
+            s.env.done[k - 1].copy_(self.done_step, non_blocking=True)
+        self.in_reward.copy_(self.all_reward[k], non_blocking=True)
+        if zero_inputs_on_done:                                                   # action_server.py:49-53
+            self.in_action.masked_fill_(self.done_step, 0)
+            self.in_reward.masked_fill_(self.done_step, 0)
+        return obs_dst
+
+    def begin_batch(self):
+        """Row 0 of prev_action is what the agent saw as previous action when the batch starts
+        (gpu/collectors.py:23-24)."""
+        self.all_action[0].copy_(self.in_action, non_blocking=True)
+
+    # ---- agent.step on resident data ---------------------------------------------------------------
+    @torch.no_grad()
+    def act(self, t, obs_dev, blank_done_rows=False):
+        step = self.agent.step(obs_dev, self.in_action, self.in_reward)
+        action, agent_info = step.action, step.agent_info
+        if blank_done_rows:  # wait-reset collectors record blanks for finished envs
+            keep = ~self.done_step
+            action = action * keep
+            agent_info = _mask_rows(agent_info, keep)
+        self.samples.agent.action[t].copy_(action, non_blocking=True)
+        self.samples.agent.agent_info[t] = agent_info
+        self.in_action.copy_(action, non_blocking=True)
+        self.step_pyt.action.copy_(action, non_blocking=True)                    # D2H for the envs
+        self.stream.synchronize()                                                 # actions are on the host
+
+    def zero_inputs_where_done(self):
+        self.in_action.masked_fill_(self.done_step, 0)
+        self.in_reward.masked_fill_(self.done_step, 0)
+
+    @torch.no_grad()
+    def bootstrap(self, obs_dev):
+        if "bootstrap_value" in self.samples.agent:
+            self.samples.agent.bootstrap_value[0].copy_(
+                self.agent.value(obs_dev, self.in_action, self.in_reward), non_blocking=True)
+
+
+def _mask_rows(buf, keep):
+    """Zero the rows (leading dim B) of every tensor of a namedarraytuple where ``keep`` is False."""
+    if isinstance(buf, torch.Tensor):
+        k = keep.view((-1,) + (1,) * (buf.dim() - 1))
+        return buf * k.to(buf.dtype)
+    return buf._make(tuple(_mask_rows(b, keep) for b in buf))

@@ -1,0 +1,40 @@
+"""Python face of the indexed row-gather kernels (csrc/gather.cu)."""
+import ctypes
+
+import torch
+
+from rlpyt_b200 import _lib
+
+
+def gather_rows(src, idx, out=None):
+    """``src.view(R, -1)[idx]`` for a contiguous CUDA tensor ``src`` whose first dim is the row
+    dim; ``idx`` int64 CUDA.  Returns ``[len(idx), *src.shape[1:]]``."""
+    _lib.require_cuda(src, idx)
+    assert src.is_contiguous() and idx.dtype == torch.int64 and idx.is_contiguous()
+    n = idx.numel()
+    row_bytes = (src.numel() // max(1, src.shape[0])) * src.element_size()
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.call("rl_gather_rows", _lib.ptr(src), _lib.ptr(idx), _lib.ptr(out), n, row_bytes, _lib.stream())
+    return out
+
+
+def gather_rows_multi(srcs, idx, outs=None):
+    """Gather several small fields (row size a multiple of 4 bytes; bool/uint8 fields are not
+    eligible) with one index vector in ONE launch.  ``srcs``: list of contiguous CUDA tensors
+    sharing the leading (row) dim."""
+    n = idx.numel()
+    k = len(srcs)
+    assert 1 <= k <= 8
+    if outs is None:
+        outs = [torch.empty((n,) + tuple(s.shape[1:]), dtype=s.dtype, device=s.device) for s in srcs]
+    src_arr = (ctypes.c_void_p * k)(*[s.data_ptr() for s in srcs])
+    dst_arr = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
+    rb_arr = (ctypes.c_int64 * k)(*[(s.numel() // max(1, s.shape[0])) * s.element_size() for s in srcs])
+    for s in srcs:
+        _lib.require_cuda(s)
+        assert s.is_contiguous()
+    with torch.cuda.device(idx.device):
+        _lib.call("rl_gather_rows_multi", k, src_arr, dst_arr, rb_arr, _lib.ptr(idx), n, _lib.stream())
+    return outs

@@ -152,7 +152,187 @@ def gen_returns():
     _save("returns", out)
 
 
-GROUPS = {"returns": gen_returns}
+
+# --------------------------------------------------------------------------- pg loss
+def loss_inputs(seed, N, A, with_valid, zero_adv_frac=0.05):
+    """Synthetic minibatch for the loss kernels (N=8192, A=6)."""
+    rng = np.random.default_rng(seed)
+    logits = rng.standard_normal((N, A)).astype(np.float32)
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    p_new = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    logits_old = logits + 0.15 * rng.standard_normal((N, A)).astype(np.float32)
+    e = np.exp(logits_old - logits_old.max(-1, keepdims=True))
+    p_old = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    same = rng.random(N) < 0.1          # ratio exactly 1 on some rows
+    p_old[same] = p_new[same]
+    value = rng.standard_normal(N).astype(np.float32)
+    action = rng.integers(0, A, size=N).astype(np.int64)
+    adv = rng.standard_normal(N).astype(np.float32)
+    adv[rng.random(N) < zero_adv_frac] = 0.0
+    ret = rng.standard_normal(N).astype(np.float32)
+    valid = (rng.random(N) < 0.8).astype(np.float32) if with_valid else None
+    return p_new, p_old, value, action, adv, ret, valid
+
+
+LOSS_CASES = [
+    # name, seed, N, A, with_valid, clip, c_v, c_ent
+    ("kat", None, 4, 3, False, 0.1, 1.0, 0.01),
+    ("kat_valid", None, 4, 3, True, 0.1, 1.0, 0.01),
+    ("n37_a18", 21, 37, 18, False, 0.2, 0.5, 0.01),
+    ("n37_a18_valid", 22, 37, 18, True, 0.2, 0.5, 0.01),
+    ("a2c_cfg", 23, 1280, 6, False, 0.1, 0.5, 0.01),
+    ("a2c_cfg_valid", 24, 1280, 6, True, 0.1, 0.5, 0.01),
+    ("ppo_cfg", 25, 8192, 6, False, 0.1, 1.0, 0.01),
+    ("ppo_cfg_valid", 26, 8192, 6, True, 0.1, 1.0, 0.01),
+    ("n1", 27, 1, 4, False, 0.1, 1.0, 0.01),
+]
+
+
+def gen_loss():
+    import torch
+    from rlpyt.algos.pg.ppo import PPO
+    from rlpyt.algos.pg.a2c import A2C
+    from rlpyt.distributions.categorical import Categorical, DistInfo
+    from rlpyt.agents.base import AgentInputs
+    from collections import namedtuple
+
+    class StubAgent:
+        """Stands in for the network: returns fixed (prob, value) leaves so the reference's own
+        PPO.loss / A2C.loss arithmetic and autograd run unmodified."""
+        recurrent = False
+
+        def __init__(self, p, v, A):
+            self.p, self.v = p, v
+            self.distribution = Categorical(dim=A)
+
+        def __call__(self, observation, prev_action, prev_reward):
+            return DistInfo(prob=self.p), self.v
+
+    out = {}
+    for name, seed, N, A, with_valid, clip, c_v, c_ent in LOSS_CASES:
+        if name.startswith("kat"):  # SURVEY.md 9.2
+            p_new = np.array([[.2, .5, .3], [.6, .3, .1], [.1, .1, .8], [.25, .25, .5]], np.float32)
+            p_old = np.array([[.3, .4, .3], [.5, .4, .1], [.2, .2, .6], [.25, .25, .5]], np.float32)
+            value = np.array([.5, -.2, 1, 0], np.float32)
+            action = np.array([1, 0, 2, 1], np.int64)
+            adv = np.array([1, -.5, 2, .3], np.float32)
+            ret = np.array([1, 0, .5, -.4], np.float32)
+            valid = np.array([1, 1, 0, 1], np.float32) if with_valid else None
+        else:
+            p_new, p_old, value, action, adv, ret, valid = loss_inputs(seed, N, A, with_valid)
+        for k, x in dict(p_new=p_new, p_old=p_old, value=value, action=action, adv=adv, ret=ret).items():
+            out[f"{name}/{k}"] = x
+        if valid is not None:
+            out[f"{name}/valid"] = valid
+        out[f"{name}/hyper"] = np.array([clip, c_v, c_ent], np.float64)
+        # ---- PPO.loss through the reference class
+        p = torch.from_numpy(p_new).clone().requires_grad_(True)
+        v = torch.from_numpy(value).clone().requires_grad_(True)
+        algo = PPO(value_loss_coeff=c_v, entropy_loss_coeff=c_ent, ratio_clip=clip)
+        algo.agent = StubAgent(p, v, A)
+        dummy = AgentInputs(torch.zeros(N), torch.zeros(N), torch.zeros(N))
+        loss, entropy, perplexity = algo.loss(
+            dummy, torch.from_numpy(action), torch.from_numpy(ret), torch.from_numpy(adv),
+            None if valid is None else torch.from_numpy(valid), DistInfo(prob=torch.from_numpy(p_old)))
+        loss.backward()
+        out[f"{name}/ppo/scalars"] = np.array([loss.item(), entropy.item(), perplexity.item()], np.float64)
+        out[f"{name}/ppo/grad_prob"] = p.grad.numpy().copy()
+        out[f"{name}/ppo/grad_value"] = v.grad.numpy().copy()
+        # ---- A2C.loss: the reference method also calls process_returns(samples); feed it
+        # pre-computed (return_, advantage, valid) by overriding that one method on the instance.
+        p = torch.from_numpy(p_new).clone().requires_grad_(True)
+        v = torch.from_numpy(value).clone().requires_grad_(True)
+        a2c = A2C(value_loss_coeff=c_v, entropy_loss_coeff=c_ent)
+        a2c.agent = StubAgent(p, v, A)
+        a2c.process_returns = lambda samples: (torch.from_numpy(ret), torch.from_numpy(adv),
+                                               None if valid is None else torch.from_numpy(valid))
+        S = namedtuple("S", "env agent")
+        E = namedtuple("E", "observation prev_reward")
+        Ag = namedtuple("Ag", "prev_action action")
+        samples = S(E(torch.zeros(N), torch.zeros(N)), Ag(torch.zeros(N), torch.from_numpy(action)))
+        loss, entropy, perplexity = a2c.loss(samples)
+        loss.backward()
+        out[f"{name}/a2c/scalars"] = np.array([loss.item(), entropy.item(), perplexity.item()], np.float64)
+        out[f"{name}/a2c/grad_prob"] = p.grad.numpy().copy()
+        out[f"{name}/a2c/grad_value"] = v.grad.numpy().copy()
+    _save("loss", out)
+
+
+# --------------------------------------------------------------------------- PPO / A2C iteration
+def rollout_inputs(seed, T, B, image_shape, A):
+    """A synthetic [T,B] batch as the sampler would hand it to the algorithm."""
+    rng = np.random.default_rng(seed)
+    obs = rng.integers(0, 256, size=(T, B) + tuple(image_shape), dtype=np.uint8)
+    action = rng.integers(0, A, size=(T, B)).astype(np.int64)
+    reward = rng.choice(np.array([-1, 0, 1], np.float32), size=(T, B), p=[0.1, 0.8, 0.1]).astype(np.float32)
+    done = rng.random((T, B)) < 0.05
+    value = rng.standard_normal((T, B)).astype(np.float32) * 0.1
+    logits = rng.standard_normal((T, B, A)).astype(np.float32) * 0.3
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    old_prob = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    bv = rng.standard_normal((1, B)).astype(np.float32) * 0.1
+    return obs, action, reward, done, value, old_prob, bv
+
+
+def gen_ppo():
+    """Two iterations of the reference PPO / one of A2C on a tiny AtariFf problem, CPU."""
+    import torch
+    from collections import namedtuple
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import atari_ff
+    from rlpyt.algos.pg.ppo import PPO
+    from rlpyt.algos.pg.a2c import A2C
+    from rlpyt.agents.pg.atari import AtariFfAgent
+    from rlpyt.samplers.collections import Samples, AgentSamplesBsv, EnvSamples, BatchSpec
+    from rlpyt.agents.pg.base import AgentInfo
+    from rlpyt.distributions.categorical import DistInfo
+    Spaces = namedtuple("Spaces", "observation action")
+    Obs = namedtuple("Obs", "shape")
+    Act = namedtuple("Act", "n")
+    out = {}
+    T, B, image_shape, A = 8, 6, (4, 36, 36), 5
+    torch.set_num_threads(1)
+    for algo_name in ("ppo", "ppo_valid_norm", "a2c"):
+        sd0 = atari_ff.init_state_dict(image_shape, A, seed=3)
+        agent = AtariFfAgent(initial_model_state_dict={k: v.clone() for k, v in sd0.items()})
+        agent.initialize(Spaces(Obs(image_shape), Act(A)))
+        n_itr = 4
+        if algo_name == "a2c":
+            algo = A2C(gae_lambda=0.95, normalize_advantage=False)
+        elif algo_name == "ppo":
+            algo = PPO(gae_lambda=0.98, minibatches=2, epochs=2)
+        else:
+            algo = PPO(gae_lambda=1, minibatches=3, epochs=2, normalize_advantage=True, ratio_clip=0.2)
+        mbr = algo_name != "ppo_valid_norm"
+        algo.initialize(agent, n_itr, BatchSpec(T, B), mid_batch_reset=mbr)
+        np.random.seed(77)
+        out[f"{algo_name}/sd0_seed"] = np.array([3])  # atari_ff.init_state_dict(image_shape, A, seed=3)
+        out[f"{algo_name}/sd0_check"] = np.array([float(sum(v.double().sum() for v in sd0.values()))])
+        for itr in range(2):
+            obs, action, reward, done, value, old_prob, bv = rollout_inputs(100 + itr, T, B, image_shape, A)
+            for k, x in dict(obs=obs, action=action, reward=reward, done=done, value=value,
+                             old_prob=old_prob, bv=bv).items():
+                out[f"{algo_name}/itr{itr}/{k}"] = x
+            t = torch.from_numpy
+            all_action = torch.cat([torch.zeros(1, B, dtype=torch.int64), t(action)])
+            all_reward = torch.cat([torch.zeros(1, B), t(reward)])
+            samples = Samples(
+                agent=AgentSamplesBsv(action=all_action[1:], prev_action=all_action[:-1],
+                                      agent_info=AgentInfo(dist_info=DistInfo(prob=t(old_prob)), value=t(value)),
+                                      bootstrap_value=t(bv)),
+                env=EnvSamples(observation=t(obs), reward=all_reward[1:], prev_reward=all_reward[:-1],
+                               done=t(done), env_info=None))
+            agent.train_mode(itr)
+            info = algo.optimize_agent(itr, samples)
+            for f in ("loss", "gradNorm", "entropy", "perplexity"):
+                out[f"{algo_name}/itr{itr}/opt_{f}"] = np.atleast_1d(np.asarray(getattr(info, f), np.float64))
+            for k, v in agent.state_dict().items():  # fc weight: first 8 rows only (fixture size)
+                a = v.detach().numpy().copy()
+                out[f"{algo_name}/itr{itr}/sd/{k}"] = a[:8] if k == "conv.head.model.0.weight" else a
+    _save("ppo", out)
+
+
+GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo}
 
 
 def main():
