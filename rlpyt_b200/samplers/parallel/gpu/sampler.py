@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from rlpyt_b200.samplers.base import BaseSampler
-from rlpyt_b200.samplers.buffer import build_samples_buffer, pin_shared, StepBuffer
+from rlpyt_b200.samplers.buffer import build_samples_buffer, pin_shared, unpin_shared, StepBuffer
 from rlpyt_b200.samplers.collectors import GpuResetCollector
 from rlpyt_b200.samplers.rollout import DeviceRollout
 from rlpyt_b200.utils.collections import AttrDict
@@ -156,6 +156,11 @@ class GpuSampler(BaseSampler):
         self.ctrl.barrier_in.wait()
         for w in self.workers:
             w.join(timeout=10)
+        torch.cuda.synchronize(self.device)
+        if self.host.get("pinned"):
+            for a in self.host["step_np"]:
+                unpin_shared(a)
+            self.host["pinned"] = False
 
     # ------------------------------------------------------------------ action server
     def serve_actions(self, itr):

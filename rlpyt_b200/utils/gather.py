@@ -15,6 +15,8 @@ def gather_rows(src, idx, out=None):
     row_bytes = (src.numel() // max(1, src.shape[0])) * src.element_size()
     if out is None:
         out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if n == 0:
+        return out
     with torch.cuda.device(src.device):
         _lib.call("rl_gather_rows", _lib.ptr(src), _lib.ptr(idx), _lib.ptr(out), n, row_bytes, _lib.stream())
     return out

@@ -332,7 +332,120 @@ def gen_ppo():
     _save("ppo", out)
 
 
-GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo}
+# --------------------------------------------------------------------------- replay
+def replay_stream(seed, n_batches, T, B, obs_shape, A, p_done):
+    """Consecutive sampler batches with proper frame history (frame c of step t = frame c+1 of t-1)."""
+    rng = np.random.default_rng(seed)
+    nf = obs_shape[0]
+    hist = rng.integers(0, 256, size=(nf - 1, B) + tuple(obs_shape[1:]), dtype=np.uint8)
+    for _ in range(n_batches):
+        new = rng.integers(0, 256, size=(T, B) + tuple(obs_shape[1:]), dtype=np.uint8)
+        full = np.concatenate([hist, new], 0)                       # [T+nf-1,B,H,W]
+        obs = np.stack([full[c:c + T] for c in range(nf)], axis=2)   # [T,B,nf,H,W]
+        hist = full[-(nf - 1):] if nf > 1 else hist
+        yield dict(observation=obs, action=rng.integers(0, A, size=(T, B)).astype(np.int64),
+                   reward=rng.standard_normal((T, B)).astype(np.float32), done=rng.random((T, B)) < p_done)
+
+
+REPLAY_CASES = [
+    # name, seed, size, B, obs_shape, n_step, discount, batch_T, n_batches, batch_B, prioritized, unique
+    ("kat", 31, 16, 2, (3, 1, 1), 2, 0.5, 4, 6, 5, True, False),
+    ("small_pri", 32, 96, 4, (4, 6, 5), 3, 0.99, 5, 9, 16, True, False),
+    ("small_pri_unique", 33, 96, 4, (4, 6, 5), 3, 0.99, 5, 9, 12, True, True),
+    ("small_uni", 34, 96, 4, (4, 6, 5), 3, 0.99, 5, 9, 16, False, False),
+    ("n1_f1", 35, 60, 3, (1, 4, 4), 1, 0.9, 7, 6, 10, True, False),
+    ("mid_pri", 36, 2048, 8, (4, 12, 12), 3, 0.99, 16, 24, 64, True, False),
+    ("bigT_append", 37, 64, 4, (2, 3, 3), 5, 0.95, 13, 5, 8, True, False),
+]
+
+
+def gen_replay():
+    import torch
+    from rlpyt.replays.non_sequence.frame import PrioritizedReplayFrameBuffer, UniformReplayFrameBuffer
+    from rlpyt.replays.sum_tree import SumTree
+    from rlpyt.algos.dqn.dqn import SamplesToBuffer
+    from rlpyt.utils.logging import logger
+    logger.log = lambda *a, **k: None
+    out = {}
+    for (name, seed, size, B, obs_shape, n_step, discount, batch_T, n_batches, batch_B, prioritized,
+         unique) in REPLAY_CASES:
+        example = SamplesToBuffer(observation=np.zeros(obs_shape, np.uint8), action=np.int64(0),
+                                  reward=np.float32(0), done=np.bool_(False))
+        kw = dict(example=example, size=size, B=B, discount=discount, n_step_return=n_step)
+        buf = (PrioritizedReplayFrameBuffer(alpha=0.6, beta=0.4, default_priority=1, unique=unique, **kw)
+               if prioritized else UniformReplayFrameBuffer(**kw))
+        out[f"{name}/cfg"] = np.array([seed, size, B, n_step, batch_T, n_batches, batch_B, int(prioritized), int(unique)])
+        out[f"{name}/obs_shape"] = np.array(obs_shape)
+        out[f"{name}/discount"] = np.array([discount])
+        np.random.seed(seed)
+        rng = np.random.default_rng(seed + 1000)
+        for i, s in enumerate(replay_stream(seed, n_batches, batch_T, B, obs_shape, 4, 0.1)):
+            buf.append_samples(SamplesToBuffer(**s))
+            out[f"{name}/b{i}/t"] = np.array([buf.t])
+            if prioritized:
+                out[f"{name}/b{i}/root"] = np.array([buf.priority_tree.tree[0]])
+            if i < 2:  # too early to sample (nothing valid yet in tiny buffers)
+                continue
+            if prioritized and buf.priority_tree.tree[0] <= 0:
+                continue
+            u = rng.random(batch_B)
+            if prioritized:
+                if unique:
+                    batch = buf.sample_batch(batch_B)      # draws from np.random internally
+                else:
+                    state = np.random.get_state()
+                    np.random.rand(batch_B)                 # keep the stream position of sample()
+                    np.random.set_state(state)
+                    import rlpyt.replays.sum_tree as st
+                    orig = np.random.rand
+                    st.np.random.rand = lambda n, _u=u: _u.copy()   # inject known uniforms
+                    try:
+                        batch = buf.sample_batch(batch_B)
+                    finally:
+                        st.np.random.rand = orig
+                    out[f"{name}/b{i}/uniforms"] = u
+                tidx = buf.priority_tree.prev_tree_idxs
+                out[f"{name}/b{i}/tree_idxs"] = np.asarray(tidx).copy()
+                out[f"{name}/b{i}/is_weights"] = batch.is_weights.numpy().copy()
+            else:
+                st0 = np.random.get_state()
+                batch = buf.sample_batch(batch_B)
+                np.random.set_state(st0)
+                T_idxs, B_idxs = buf.sample_idxs(batch_B)
+                out[f"{name}/b{i}/T_idxs"], out[f"{name}/b{i}/B_idxs"] = T_idxs, B_idxs
+            flat = dict(observation=batch.agent_inputs.observation, prev_action=batch.agent_inputs.prev_action,
+                        prev_reward=batch.agent_inputs.prev_reward, action=batch.action, return_=batch.return_,
+                        done=batch.done, done_n=batch.done_n, target_observation=batch.target_inputs.observation,
+                        target_prev_action=batch.target_inputs.prev_action,
+                        target_prev_reward=batch.target_inputs.prev_reward)
+            for k, v in flat.items():
+                out[f"{name}/b{i}/{k}"] = v.numpy().copy()
+            if prioritized:
+                new_pri = np.abs(rng.standard_normal(batch_B)).astype(np.float32) + 0.01
+                out[f"{name}/b{i}/new_pri"] = new_pri
+                buf.update_batch_priorities(torch.from_numpy(new_pri))
+                out[f"{name}/b{i}/root_after"] = np.array([buf.priority_tree.tree[0]])
+        if prioritized:
+            out[f"{name}/final_tree"] = buf.priority_tree.tree.copy()
+        out[f"{name}/final_frames"] = buf.samples_frames.copy() if buf.samples_frames.size < 200000 else buf.samples_frames[:8].copy()
+        out[f"{name}/final_return"] = buf.samples_return_.copy()
+        out[f"{name}/final_done_n"] = buf.samples_done_n.copy()
+    # raw SumTree known answers of SURVEY.md 9.3
+    tree = SumTree(T=6, B=2, off_backward=2, off_forward=1, default_value=1.0)
+    for k in range(5):
+        tree.advance(2)
+        out[f"tree_kat/adv{k}"] = tree.tree.copy()
+    np.random.seed(3)
+    (T_idxs, B_idxs), pri = tree.sample(5)
+    out["tree_kat/T_idxs"], out["tree_kat/B_idxs"], out["tree_kat/pri"] = T_idxs, B_idxs, pri
+    tree.update_batch_priorities(np.array([0.5, 2.0, 3.0, 0.25, 4.0]))
+    out["tree_kat/after_update"] = tree.tree.copy()
+    idx, _ = tree.find(np.array([0, 0.1, 0.5, 0.999999, 1.0]))
+    out["tree_kat/find"] = idx
+    _save("replay", out)
+
+
+GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay}
 
 
 def main():

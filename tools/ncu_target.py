@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Small, deterministic targets for ncu (never a bench value):
+    ncu ... python tools/ncu_target.py ppo      # one PPO optimize_agent iteration on resident samples
+    ncu ... python tools/ncu_target.py gae      # GAE streaming kernel at [128, 2^20] + tscan at [128,256]
+    ncu ... python tools/ncu_target.py replay   # sum-tree sample/update + frame gather
+Profiling is limited to the region between cudaProfilerStart/Stop (use --profile-from-start off).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def resident_samples(T, B, A, dev="cuda"):
+    from rlpyt_b200.samplers.collections import Samples, AgentSamplesBsv, EnvSamples
+    from rlpyt_b200.agents.pg.base import AgentInfo
+    from rlpyt_b200.distributions.categorical import DistInfo
+    g = torch.Generator(device=dev).manual_seed(0)
+    obs = torch.randint(0, 256, (T, B) + bench.IMAGE, dtype=torch.uint8, device=dev, generator=g)
+    all_action = torch.randint(0, A, (T + 1, B), device=dev, generator=g)
+    all_reward = torch.randn(T + 1, B, device=dev, generator=g)
+    prob = torch.softmax(torch.randn(T, B, A, device=dev, generator=g), -1)
+    return Samples(
+        agent=AgentSamplesBsv(all_action[1:], all_action[:-1], AgentInfo(DistInfo(prob), torch.randn(T, B, device=dev, generator=g)),
+                              torch.randn(1, B, device=dev, generator=g)),
+        env=EnvSamples(obs, all_reward[1:], all_reward[:-1], torch.rand(T, B, device=dev, generator=g) < 0.002, None))
+
+
+def ppo():
+    from collections import namedtuple
+    from rlpyt_b200.agents.pg.atari import AtariFfAgent
+    from rlpyt_b200.algos.pg.ppo import PPO
+    from rlpyt_b200.samplers.collections import BatchSpec
+    Spaces = namedtuple("Spaces", "observation action")
+    agent = AtariFfAgent()
+    agent.initialize(Spaces(namedtuple("O", "shape")(bench.IMAGE), namedtuple("Ac", "n")(bench.N_ACTIONS)))
+    agent.to_device(0)
+    T, B = bench.T_CFG, bench.B_CFG
+    samples = resident_samples(T, B, bench.N_ACTIONS)
+    algo = PPO(**bench.PPO_KW)
+    algo.initialize(agent, 10 ** 6, BatchSpec(T, B), mid_batch_reset=True)
+    agent.train_mode(0)
+    algo.optimize_agent(0, samples)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    algo.optimize_agent(1, samples)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+def gae():
+    from rlpyt_b200.algos import utils as U
+    for (T, B, algo) in [(128, 1 << 20, 1), (128, 256, 2), (128, 256, 1)]:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        r = torch.randn(T, B, device="cuda", generator=g)
+        v = torch.randn(T, B, device="cuda", generator=g)
+        d = torch.rand(T, B, device="cuda", generator=g) < 0.01
+        b = torch.randn(1, B, device="cuda", generator=g)
+        adv, ret = torch.empty_like(r), torch.empty_like(r)
+        U.generalized_advantage_estimation(r, v, d, b, 0.99, 0.98, advantage_dest=adv, return_dest=ret, algo=algo)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        U.generalized_advantage_estimation(r, v, d, b, 0.99, 0.98, advantage_dest=adv, return_dest=ret, algo=algo)
+        U.discount_return(r, d, b, 0.99, return_dest=ret, algo=algo)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    {"ppo": ppo, "gae": gae}[sys.argv[1]]()
