@@ -16,8 +16,14 @@ SamplesFromReplayPri = namedarraytuple("SamplesFromReplayPri", SamplesFromReplay
 class PrioritizedReplay:
 
     def __init__(self, alpha=0.6, beta=0.4, default_priority=1, unique=False, input_priorities=False,
-                 input_priority_shift=0, **kwargs):
+                 input_priority_shift=0, pow_on_host=False, **kwargs):
+        """``pow_on_host``: evaluate ``priorities ** alpha`` with numpy on the host like the reference
+        (one small D2H/H2D round trip + sync per update) instead of the device kernel.  numpy's
+        float32 ``power`` is SIMD/SVML-dispatched and differs from the correctly rounded result by
+        1 ulp on ~20 % of inputs depending on the host CPU, so only this mode reproduces a recorded
+        reference stream bit-for-bit; the default device kernel returns the correctly rounded value."""
         super().__init__(**kwargs)
+        self.pow_on_host = pow_on_host
         self.alpha, self.beta = alpha, beta
         self.default_priority = default_priority
         self.unique = unique
@@ -48,6 +54,9 @@ class PrioritizedReplay:
 
     def _pow_alpha(self, priorities):
         """``priorities ** alpha`` as numpy float32 pow, widened to fp64 (prioritized.py:49,79)."""
+        if getattr(self, "pow_on_host", False):
+            host = priorities.detach().cpu().numpy() if isinstance(priorities, torch.Tensor) else np.asarray(priorities)
+            return torch.from_numpy((host ** self.alpha).astype(np.float64)).to(self.device)
         p = torch.as_tensor(priorities).to(self.device, dtype=torch.float32).contiguous()
         out = torch.empty(p.shape, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):

