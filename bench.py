@@ -119,15 +119,17 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    cores = len(os.sched_getaffinity(0))
-    n_workers = args.workers or max(1, min(32, cores // world - 2, B_CFG))
+    all_cpus = sorted(os.sched_getaffinity(0))
+    cores = len(all_cpus)
+    n_workers = args.workers or max(1, min(32, cores // (2 * world) - 1, B_CFG))
     seed = 0 + 100 * rank                                            # sync_rl.py:82 seeds per rank
     np.random.seed(seed)
     torch.manual_seed(seed)
     sampler = GpuSampler(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
                          max_decorrelation_steps=20)
     agent = AtariFfAgent()
-    affinity = dict(cuda_idx=local_rank, workers_cpus=[None] * n_workers, set_affinity=False)
+    from rlpyt_b200.utils.affinity import make_affinity
+    affinity = make_affinity(local_rank, n_workers, local_rank=local_rank, ranks_per_node=world, reserve_master=4)
     sampler.initialize(agent, affinity=affinity, seed=seed + 1, bootstrap_value=True, world_size=world, rank=rank)
     agent.to_device(local_rank)
     if world > 1:
@@ -187,6 +189,10 @@ def run_b200(args):
         d2h = T_CFG * B_CFG * 8 + 16 * 4 * 4
     finally:
         sampler.shutdown()
+        try:
+            os.sched_setaffinity(0, all_cpus)  # the sampler pinned the master near its GPU; undo for the CPU legs
+        except OSError:
+            pass
 
     out = {
         "metric": "env-steps/sec PPO Atari [T=128,B=256] at 1/2/4/8 GPU; GAE-scan GB/s",

@@ -39,6 +39,12 @@ const char* rl_b200_last_error(void);
 /* Number of SMs of the current device (148 on B200); <0 on error.  Host-side helper. */
 int rl_b200_sm_count(void);
 
+/* HOST helper for the env workers (rlpyt/samplers/parallel/gpu/collectors.py:38 writes
+ * step.observation[b] = o): copy nbytes from src to the page-locked step buffer with
+ * non-temporal stores so the GPU's DMA does not have to snoop the worker cores' caches.
+ * Host pointers; no CUDA call inside; safe in forked worker processes. */
+int rl_host_stream_copy(void* dst, const void* src, int64_t nbytes);
+
 /* ------------------------------------------------------------------ returns (K1-K4)
  * algo: 0 = auto, 1 = streaming column kernel (thread per 1/4 columns, sequential in t,
  *       reference operation order => bit-identical to the reference),

@@ -11,5 +11,8 @@ import torch as _torch
 # fp32 parity with the reference (which predates TF32): keep cuDNN / cuBLAS in true fp32.
 _torch.backends.cudnn.allow_tf32 = False
 _torch.backends.cuda.matmul.allow_tf32 = False
+# Let cuDNN time its fp32 algorithms once per shape: the default heuristic picks a 3x slower
+# implicit-GEMM for the 4-channel 8x8/stride-4 first layer (profiles/r01_profile_step_first.txt).
+_torch.backends.cudnn.benchmark = True
 
 __version__ = "0.1.0"

@@ -21,6 +21,7 @@ SIGNATURES = {
     "rl_b200_abi_version": (c_int, []),
     "rl_b200_last_error": (c_char_p, []),
     "rl_b200_sm_count": (c_int, []),
+    "rl_host_stream_copy": (c_int, [P, P, c_int64]),
     "rl_gae_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_float, c_int, P]),
     "rl_discount_return_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_int, P]),
     "rl_nstep_return_f32": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, P]),
@@ -108,3 +109,13 @@ def call(name, *args, n_launch=1):
     rc = getattr(load(), name)(*args)
     check(rc, name)
     launch_count += n_launch
+
+
+def host_stream_copy(dst, src):
+    """numpy -> numpy copy with non-temporal stores (see rl_host_stream_copy).  Falls back to a
+    plain assignment for non-contiguous / mismatched arrays."""
+    if (dst.flags["C_CONTIGUOUS"] and getattr(src, "flags", None) is not None and src.flags["C_CONTIGUOUS"]
+            and dst.nbytes == src.nbytes and dst.dtype == src.dtype):
+        load().rl_host_stream_copy(dst.ctypes.data, src.ctypes.data, dst.nbytes)
+    else:
+        dst[...] = src

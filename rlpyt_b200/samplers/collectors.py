@@ -9,6 +9,8 @@ the next observation, reward and done into the step buffer and ``env_info`` into
 """
 import numpy as np
 
+from rlpyt_b200._lib import host_stream_copy
+
 
 class DecorrelatingStartCollector:
 
@@ -71,7 +73,7 @@ class GpuResetCollector(DecorrelatingStartCollector):
                     completed.append(traj_infos[b].terminate(o))
                     traj_infos[b] = self.TrajInfoCls()
                     o = env.reset()
-                step.observation[b] = o
+                host_stream_copy(step.observation[b], o)  # non-temporal: keep the DMA source out of this core's L2
                 step.reward[b] = r
                 step.done[b] = d
                 if env_info:

@@ -89,6 +89,8 @@ class GpuSampler(BaseSampler):
             cuda_idx = torch.cuda.current_device()
         self.device = torch.device("cuda", cuda_idx)
 
+        from rlpyt_b200 import _lib
+        _lib.load()  # before the fork: workers use its host-side streaming copy
         env = self.EnvCls(**self.env_kwargs)
         agent.initialize(env.spaces, share_memory=False, global_B=global_B, env_ranks=env_ranks)
         self.agent = agent
@@ -116,8 +118,10 @@ class GpuSampler(BaseSampler):
                       max_decorrelation_steps=self.max_decorrelation_steps, global_B=global_B)
         step_np, env_info_np = self.host["step_np"], self.host["env_info_np"]
         self.workers, i_env, g_env = [], 0, B * rank
+        self.worker_slices = []
         for w_rank, n_envs in enumerate(n_envs_list):
             sl = slice(i_env, i_env + n_envs)
+            self.worker_slices.append(sl)
             wk = dict(rank=w_rank, env_ranks=list(range(g_env, g_env + n_envs)),
                       seed=None if seed is None else seed + w_rank,
                       cpus=workers_cpus[w_rank] if affinity.get("set_affinity", True) else None,
@@ -132,6 +136,11 @@ class GpuSampler(BaseSampler):
             w.start()
         if not self.host["pinned"]:  # page-lock after the fork so the children never see CUDA state
             self.host["pinned"] = all(pin_shared(a) for a in step_np)
+        if affinity.get("set_affinity", True) and affinity.get("master_cpus"):
+            try:
+                os.sched_setaffinity(0, affinity["master_cpus"])
+            except (AttributeError, OSError):
+                pass
         self.ctrl.barrier_out.wait()  # workers decorrelated, first observations are in the step buffer
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)

@@ -28,12 +28,22 @@ class DeviceRollout:
         self.stream = torch.cuda.current_stream(device)
 
     # ---- H2D of what the envs produced since the last step ---------------------------------------
-    def upload(self, k, zero_inputs_on_done):
+    def obs_slot(self, k):
+        """Where observation(k) lives in HBM: row k of the batch, or the bootstrap slot for k == T."""
+        return self.samples.env.observation[k] if k < self.T else self.obs_extra
+
+    def upload_obs_chunk(self, obs_dst, sl):
+        """Async H2D of one worker's rows as soon as that worker is done (its DMA overlaps the
+        workers still stepping)."""
+        obs_dst[sl].copy_(self.step_pyt.observation[sl], non_blocking=True)
+
+    def upload(self, k, zero_inputs_on_done, obs_done=False):
         """Event k (0..T): the envs have written observation(k), reward(k-1), done(k-1) into the
         step buffer.  Record them at their [T,B] rows and stage the agent inputs."""
         s = self.samples
-        obs_dst = s.env.observation[k] if k < self.T else self.obs_extra
-        obs_dst.copy_(self.step_pyt.observation, non_blocking=True)
+        obs_dst = self.obs_slot(k)
+        if not obs_done:
+            obs_dst.copy_(self.step_pyt.observation, non_blocking=True)
         self.all_reward[k].copy_(self.step_pyt.reward, non_blocking=True)       # reward(k-1) = prev_reward(k)
         self.done_step.copy_(self.step_pyt.done, non_blocking=True)
         if k >= 1:
