@@ -121,7 +121,8 @@ def run_b200(args):
 
     all_cpus = sorted(os.sched_getaffinity(0))
     cores = len(all_cpus)
-    n_workers = args.workers or max(1, min(32, cores // (2 * world) - 1, B_CFG))
+    # every GPU gets the same host share at every N: one eighth of the box (an 8-GPU node)
+    n_workers = args.workers or max(1, min(B_CFG, cores // 8 - 2))
     seed = 0 + 100 * rank                                            # sync_rl.py:82 seeds per rank
     np.random.seed(seed)
     torch.manual_seed(seed)
