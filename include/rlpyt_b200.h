@@ -176,6 +176,23 @@ int rl_replay_extract(const uint8_t* frames, const int64_t* action, const float*
                       uint8_t* out_done, uint8_t* out_done_n, int64_t* out_target_prev_action,
                       float* out_target_prev_reward, void* stream);
 
+/* ------------------------------------------------------------------ AtariFf first layer on uint8 frames
+ * img.float().mul_(1/255) -> Conv2d(4->16, k8, s4, p0) -> ReLU : rlpyt/models/pg/atari_ff_model.py:50-53,
+ * rlpyt/models/conv2d.py:36-44, fused with the minibatch row gather of rlpyt/algos/pg/ppo.py:99-100.
+ * obs: [R, 4, H, W] u8 (W % 4 == 0); rows: N int64 indices into R, or NULL (= 0..N-1);
+ * weight [16,4,8,8], bias [16] f32; out [N,16,OH,OW] f32 with OH=(H-8)/4+1, OW=(W-8)/4+1.
+ * relu != 0 applies max(.,0). */
+int rl_conv1_u8_forward(const uint8_t* obs, const int64_t* rows, const float* weight, const float* bias,
+                        float* out, int64_t N, int C, int H, int W, int relu, void* stream);
+/* Weight / bias gradient of the same layer (what autograd's ConvolutionBackward + ThresholdBackward
+ * produce for it): g = grad_out * (out > 0) if relu; grad_weight[16,4,8,8] = sum g (x) x/255,
+ * grad_bias[16] = sum g.  Deterministic (fixed reduction order).  scratch:
+ * rl_conv1_u8_wgrad_scratch_bytes() bytes. */
+int64_t rl_conv1_u8_wgrad_scratch_bytes(void);
+int rl_conv1_u8_wgrad(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                      float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, int relu,
+                      void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

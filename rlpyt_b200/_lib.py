@@ -41,6 +41,9 @@ SIGNATURES = {
     "rl_is_weights_f32": (c_int, [P, c_double, P, c_int, P]),
     "rl_replay_extract": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_int64,
                                   P, P, P, P, P, P, P, P, P, P, P]),
+    "rl_conv1_u8_forward": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "rl_conv1_u8_wgrad_scratch_bytes": (c_int64, []),
+    "rl_conv1_u8_wgrad": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "rl_a2c_loss_f32": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_float, c_float, P, P, P, P, P]),
 }
 

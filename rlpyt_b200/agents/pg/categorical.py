@@ -6,6 +6,7 @@ from rlpyt_b200.agents.base import AgentStep, BaseAgent
 from rlpyt_b200.agents.pg.base import AgentInfo
 from rlpyt_b200.distributions.categorical import Categorical, DistInfo
 from rlpyt_b200.utils.buffer import buffer_to
+from rlpyt_b200.utils.gather import LazyRows
 
 
 class CategoricalPgAgent(BaseAgent):
@@ -17,6 +18,8 @@ class CategoricalPgAgent(BaseAgent):
 
     def _model_inputs(self, observation, prev_action, prev_reward):
         prev_action = self.distribution.to_onehot(prev_action)  # categorical.py:21,35
+        if isinstance(observation, LazyRows):  # un-gathered minibatch rows, already on the device
+            return (observation,) + buffer_to((prev_action, prev_reward), device=self.device)
         return buffer_to((observation, prev_action, prev_reward), device=self.device)
 
     def __call__(self, observation, prev_action, prev_reward):

@@ -18,7 +18,7 @@ from rlpyt_b200.algos.optim import FlatAdam
 from rlpyt_b200.algos.pg import loss_ops
 from rlpyt_b200.algos.pg.base import PolicyGradientAlgo, OptInfo
 from rlpyt_b200.utils.collections import namedarraytuple
-from rlpyt_b200.utils.gather import gather_rows, gather_rows_multi
+from rlpyt_b200.utils.gather import gather_rows, gather_rows_multi, LazyRows
 from rlpyt_b200.utils.misc import iterate_mb_idxs
 
 LossInputs = namedarraytuple("LossInputs",
@@ -79,13 +79,15 @@ class PPO(PolicyGradientAlgo):
         n_updates = self.epochs * (batch_size // mb_size)
         stats = torch.zeros((n_updates, 4), dtype=torch.float32, device=dev)
         fused_opt = isinstance(self.optimizer, FlatAdam)
+        lazy_obs = bool(getattr(self.agent.model, "accepts_lazy_rows", False)) and obs_f.dtype == torch.uint8
         u = 0
         for _ in range(self.epochs):                                   # ppo.py:92
             for idxs in iterate_mb_idxs(batch_size, mb_size, shuffle=True):   # ppo.py:93
                 rows_np = (idxs % T) * B + (idxs // T)                 # ppo.py:94-95: [T_idxs, B_idxs]
                 rows = torch.from_numpy(rows_np).to(dev, non_blocking=True)
                 self.optimizer.zero_grad()                             # ppo.py:96
-                obs_mb = gather_rows(obs_f, rows)
+                # models that read rows in place (fused first layer) get the un-gathered view
+                obs_mb = LazyRows(obs_f, rows) if lazy_obs else gather_rows(obs_f, rows)
                 got = gather_rows_multi(small, rows)
                 pa_mb, pr_mb, act_mb, ret_mb, adv_mb, oldp_mb = got[:6]
                 valid_mb = got[6] if valid is not None else None

@@ -1,0 +1,64 @@
+"""``Conv2d(4->16, k8, s4) + ReLU`` on uint8 frames as one autograd op over the hand-written kernels
+of csrc/conv1.cu (forward fused with the row gather and the ``/255`` scaling; backward = weight and
+bias gradients - the input is an observation and needs none)."""
+import torch
+
+from rlpyt_b200 import _lib
+
+_SCRATCH = {}
+
+
+def supported(image_shape, conv_layers):
+    """True when the model's first layers are exactly the reference default the kernel implements
+    (rlpyt/models/pg/atari_ff_model.py:31-35: channels[0]=16, kernel 8, stride 4, padding 0, ReLU)."""
+    c, h, w = image_shape
+    first = conv_layers[0] if len(conv_layers) else None
+    return (isinstance(first, torch.nn.Conv2d) and c == 4 and w % 4 == 0 and (c * h * w) % 16 == 0
+            and first.out_channels == 16 and tuple(first.kernel_size) == (8, 8) and tuple(first.stride) == (4, 4)
+            and tuple(first.padding) == (0, 0) and tuple(first.dilation) == (1, 1) and first.groups == 1
+            and len(conv_layers) > 1 and isinstance(conv_layers[1], torch.nn.ReLU))
+
+
+class Conv1U8Relu(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, weight, bias, obs, rows):
+        """obs: [R,4,H,W] uint8 CUDA contiguous; rows: int64 [N] or None -> [N,16,OH,OW] fp32."""
+        _lib.require_cuda(weight, bias, obs, rows)
+        R, C, H, W = obs.shape
+        N = R if rows is None else rows.numel()
+        OH, OW = (H - 8) // 4 + 1, (W - 8) // 4 + 1
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        out = torch.empty((N, 16, OH, OW), dtype=torch.float32, device=obs.device)
+        with torch.cuda.device(obs.device):
+            _lib.call("rl_conv1_u8_forward", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
+                      N, C, H, W, 1, _lib.stream())
+        ctx.obs, ctx.rows = obs, rows
+        ctx.save_for_backward(out)
+        ctx.mark_non_differentiable()
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (out,) = ctx.saved_tensors
+        obs, rows = ctx.obs, ctx.rows
+        R, C, H, W = obs.shape
+        N = out.shape[0]
+        dev = obs.device
+        key = str(dev)
+        scratch = _SCRATCH.get(key)
+        if scratch is None:
+            nbytes = int(_lib.load().rl_conv1_u8_wgrad_scratch_bytes())
+            scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            _SCRATCH[key] = scratch
+        gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
+        gb = torch.empty(16, dtype=torch.float32, device=dev)
+        g = grad_out.contiguous()
+        with torch.cuda.device(dev):
+            _lib.call("rl_conv1_u8_wgrad", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(gw),
+                      _lib.ptr(gb), N, C, H, W, 1, _lib.ptr(scratch), _lib.stream(), n_launch=2)
+        return gw, gb, None, None
+
+
+def conv1_u8_relu(weight, bias, obs, rows=None):
+    return Conv1U8Relu.apply(weight, bias, obs, rows)

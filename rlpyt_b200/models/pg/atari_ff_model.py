@@ -8,7 +8,9 @@ are converted with ``float(x) * (1/255)`` - one fp32 rounding, exactly the refer
 import torch
 import torch.nn.functional as F
 
+from rlpyt_b200.models import conv1_op
 from rlpyt_b200.models.conv2d import Conv2dHeadModel
+from rlpyt_b200.utils.gather import LazyRows
 from rlpyt_b200.utils.tensor import infer_leading_dims, restore_leading_dims
 
 
@@ -29,9 +31,31 @@ class AtariFfModel(torch.nn.Module):
         )
         self.pi = torch.nn.Linear(self.conv.output_size, output_size)
         self.value = torch.nn.Linear(self.conv.output_size, 1)
+        # uint8 CUDA frames take the hand-written first layer (csrc/conv1.cu) when the layer is the
+        # reference default; anything else goes through the generic torch path below.
+        self.fused_first_layer = conv1_op.supported(self.image_shape, list(self.conv.conv.conv))
+        self.accepts_lazy_rows = True
+
+    def _fused_forward(self, obs, rows, lead_shape):
+        layers = self.conv.conv.conv
+        x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, obs, rows)
+        x = layers[2:](x)
+        fc_out = self.conv.head(x.view(x.shape[0], -1))
+        pi = F.softmax(self.pi(fc_out), dim=-1)
+        v = self.value(fc_out).squeeze(-1)
+        return pi.view(lead_shape + pi.shape[1:]), v.view(lead_shape)
 
     def forward(self, image, prev_action, prev_reward):
         """[T,B,C,H,W] / [B,C,H,W] / [C,H,W] uint8 -> (pi, v) with the same leading dims."""
+        if isinstance(image, LazyRows):
+            if self.fused_first_layer and image.dtype == torch.uint8:
+                return self._fused_forward(image.src.view((-1,) + self.image_shape), image.rows,
+                                           (image.rows.numel(),))
+            image = image.materialize()
+        if (self.fused_first_layer and image.dtype == torch.uint8 and image.is_cuda
+                and image.is_contiguous() and image.dim() >= 3):
+            lead_shape = tuple(image.shape[:-3])
+            return self._fused_forward(image.view((-1,) + self.image_shape), None, lead_shape)
         img = image.type(torch.float)
         img = img.mul_(1. / 255)
         lead_dim, T, B, img_shape = infer_leading_dims(img, 3)

@@ -185,17 +185,13 @@ class GpuSampler(BaseSampler):
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=b)
-            obs_dev = ro.upload(t, zero_inputs_on_done=True)
-            if t == 0:
-                ro.begin_batch()
-            ro.act(t, obs_dev, blank_done_rows=wait_reset)
+            ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
             for s in act_ready:
                 s.release()
         for s in obs_ready:
             s.acquire()
             assert not s.acquire(block=False)  # drained (action_server.py:63)
-        obs_dev = ro.upload(T, zero_inputs_on_done=False)
-        ro.bootstrap(obs_dev)
+        ro.finish()
         if np.any(step_np.done):  # reset at end of batch; ready for the next (action_server.py:67-71)
             ended = np.where(step_np.done)[0]
             step_np.action[ended] = 0
@@ -204,6 +200,7 @@ class GpuSampler(BaseSampler):
                 self.agent.reset_one(idx=b)
             ro.zero_inputs_where_done()
         torch.cuda.current_stream(self.device).synchronize()
+        ro.end_batch()
         for s in act_ready:
             assert not s.acquire(block=False)
 

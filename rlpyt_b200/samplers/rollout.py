@@ -6,6 +6,8 @@ This is the device half of ``ActionServer.serve_actions`` (rlpyt/samplers/parall
 action_server.py:17-74) and of ``CpuResetCollector.collect_batch`` (rlpyt/samplers/parallel/cpu/
 collectors.py:25-65); the env half stays on the CPU.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -26,6 +28,12 @@ class DeviceRollout:
         self.obs_extra = torch.zeros_like(samples.env.observation[0])  # final obs (bootstrap)
         self.done_step = torch.zeros(B, dtype=torch.bool, device=device)
         self.stream = torch.cuda.current_stream(device)
+        # One CUDA graph per time step t (H2D of the step buffer -> agent.step -> record row t ->
+        # D2H of the actions): ~30 small launches become one graph launch per env step.  Captured
+        # lazily after an eager warm-up batch (cuDNN autotuning cannot run under capture).
+        self.use_graphs = os.environ.get("RLPYT_B200_SAMPLER_GRAPHS", "1") == "1"
+        self._graphs = {}
+        self._eager_batches = 0
 
     # ---- H2D of what the envs produced since the last step ---------------------------------------
     def obs_slot(self, k):
@@ -61,7 +69,7 @@ class DeviceRollout:
 
     # ---- agent.step on resident data ---------------------------------------------------------------
     @torch.no_grad()
-    def act(self, t, obs_dev, blank_done_rows=False):
+    def act(self, t, obs_dev, blank_done_rows=False, sync=True):
         step = self.agent.step(obs_dev, self.in_action, self.in_reward)
         action, agent_info = step.action, step.agent_info
         if blank_done_rows:  # wait-reset collectors record blanks for finished envs
@@ -72,7 +80,46 @@ class DeviceRollout:
         self.samples.agent.agent_info[t] = agent_info
         self.in_action.copy_(action, non_blocking=True)
         self.step_pyt.action.copy_(action, non_blocking=True)                    # D2H for the envs
-        self.stream.synchronize()                                                 # actions are on the host
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()                  # actions are on the host
+
+    # ---- one env step = upload + agent.step + record (+ D2H), optionally replayed as a CUDA graph ----
+    def _step_body(self, k, zero_inputs_on_done, blank_done_rows):
+        obs_dev = self.upload(k, zero_inputs_on_done)
+        if k == 0:
+            self.begin_batch()
+        self.act(k, obs_dev, blank_done_rows=blank_done_rows, sync=False)
+
+    def _bootstrap_body(self):
+        obs_dev = self.upload(self.T, zero_inputs_on_done=False)
+        self.bootstrap(obs_dev)
+
+    def _run(self, key, body):
+        if not (self.use_graphs and self._eager_batches >= 1 and getattr(self.agent, "device", None) is not None
+                and self.agent.device.type == "cuda"):
+            body()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+        g.replay()
+
+    def step(self, k, zero_inputs_on_done, blank_done_rows=False):
+        """Event k in [0,T): observation(k) is in the step buffer -> actions are on the host on return."""
+        self._run((k, zero_inputs_on_done, blank_done_rows),
+                  lambda: self._step_body(k, zero_inputs_on_done, blank_done_rows))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def finish(self):
+        """Event T: final observation -> bootstrap value."""
+        self._run(("bootstrap",), self._bootstrap_body)
+
+    def end_batch(self):
+        self._eager_batches += 1
 
     def zero_inputs_where_done(self):
         self.in_action.masked_fill_(self.done_step, 0)

@@ -52,10 +52,7 @@ class SerialSampler(BaseSampler):
         completed = []
         self.agent.sample_mode(itr)
         for t in range(T):
-            obs_dev = ro.upload(t, zero_inputs_on_done=False)
-            if t == 0:
-                ro.begin_batch()
-            ro.act(t, obs_dev)
+            ro.step(t, zero_inputs_on_done=False)
             for b, env in enumerate(self.envs):
                 o, r, d, env_info = env.step(step.action[b])
                 self.traj_infos[b].step(step.observation[b], step.action[b], r, d, None, env_info)
@@ -70,9 +67,9 @@ class SerialSampler(BaseSampler):
                 step.done[b] = d
                 if env_info:
                     env_info_np[t, b] = env_info
-        obs_dev = ro.upload(T, zero_inputs_on_done=False)
-        ro.bootstrap(obs_dev)
+        ro.finish()
         torch.cuda.current_stream(self.device).synchronize()
+        ro.end_batch()
         return self.samples, completed
 
     def evaluate_agent(self, itr):

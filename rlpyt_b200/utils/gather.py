@@ -40,3 +40,32 @@ def gather_rows_multi(srcs, idx, outs=None):
     with torch.cuda.device(idx.device):
         _lib.call("rl_gather_rows_multi", k, src_arr, dst_arr, rb_arr, _lib.ptr(idx), n, _lib.stream())
     return outs
+
+
+class LazyRows:
+    """``src[rows]`` that has not been gathered yet: lets a consumer that can read rows in place
+    (the fused first-layer kernel reads observations straight from the resident ``[T*B]`` batch)
+    skip materialising the 231 MB minibatch copy.  ``materialize()`` gives the plain tensor."""
+
+    def __init__(self, src, rows):
+        _lib.require_cuda(src, rows)
+        assert src.is_contiguous() and rows.dtype == torch.int64 and rows.is_contiguous()
+        self.src, self.rows = src, rows
+
+    @property
+    def shape(self):
+        return (self.rows.numel(),) + tuple(self.src.shape[1:])
+
+    @property
+    def dtype(self):
+        return self.src.dtype
+
+    @property
+    def device(self):
+        return self.src.device
+
+    def dim(self):
+        return self.src.dim()
+
+    def materialize(self):
+        return gather_rows(self.src, self.rows)
