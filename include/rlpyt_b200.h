@@ -193,6 +193,15 @@ int rl_conv1_u8_wgrad(const uint8_t* obs, const int64_t* rows, const float* out,
                       float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, int relu,
                       void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ fp32-accurate tensor-core GEMM
+ * C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ ReLU): torch.nn.Linear as used by the AtariFf fully
+ * connected layer (rlpyt/models/mlp.py:30-36 via rlpyt/models/pg/atari_ff_model.py:24-35) and its
+ * dgrad / wgrad (with transposed operands).  tcgen05.mma kind::tf32 with a 3-term hi/lo split
+ * (fp32-level accuracy), TMA-staged, accumulators in TMEM.  All row-major fp32, K %% 4 == 0,
+ * 16-byte aligned bases; bias nullable. */
+int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N,
+                       int64_t K, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,7 +86,21 @@ def bench_returns(reps):
     out(kernel="torch_copy_f32", n=n, us_med=med * 1e6, GBs=2 * 4 * n / med / 1e9)
 
 
-BENCHES = {"returns": bench_returns}
+def bench_gemm(reps):
+    from rlpyt_b200.models.gemm_op import gemm_tn
+    for name, (M, N, K) in dict(fc_fwd=(8192, 512, 3200), fc_dgrad=(8192, 3200, 512), fc_wgrad=(512, 3200, 8192),
+                                fc_step=(256, 512, 3200)).items():
+        a = torch.randn(M, K, device="cuda")
+        b = torch.randn(N, K, device="cuda")
+        med, best = timeit(lambda: gemm_tn(a, b), reps, flush=False)
+        med_t, _ = timeit(lambda: torch.mm(a, b.t()), reps, flush=False)
+        fl = 2.0 * M * N * K
+        out(kernel="gemm_tf32x3", shape=name, M=M, N=N, K=K, us_med=med * 1e6, us_best=best * 1e6,
+            eff_TFLOPs=fl / med / 1e12, tensor_TFLOPs_issued=3 * fl / med / 1e12, torch_fp32_us=med_t * 1e6,
+            speedup_vs_cublas_fp32=med_t / med)
+
+
+BENCHES = {"returns": bench_returns, "gemm": bench_gemm}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
