@@ -16,9 +16,12 @@
 //   * each thread owns 4 horizontally adjacent output positions x 16 channels = 64 fp32
 //     accumulators; per (c, ky) it reads 20 input bytes and 8x16 weights for 512 FMAs.
 // conv1_wgrad_kernel: dW[oc][k] = sum_n sum_p g[n][oc][p] * x[n][patch(p)][k], g = dY * (Y > 0):
-//   thread k owns filter tap k for all 16 channels (16 accumulators), image and masked gradient
-//   staged in shared memory ([p][oc] so the 16 channels are broadcast LDS.128); per-CTA partial sums
-//   are reduced by conv1_wgrad_reduce_kernel in CTA order => deterministic (no float atomics).
+//   thread t owns the 4 filter taps {t, t+64, t+128, t+192} (the 4 input frames at one (ky,kx)) for
+//   all 16 channels = 64 accumulators, so each broadcast load of a position's 16 gradients feeds 64
+//   FMAs (the first version, 1 tap per thread, was shared-memory-issue bound: FMA pipe 36 % busy,
+//   profiles/r01_ppo_kernels_full_summary.json); image and masked gradient are staged in shared
+//   memory ([p][oc]); per-CTA partial sums are reduced by conv1_wgrad_reduce_kernel in CTA order
+//   => deterministic (no float atomics).
 // fp32 SIMT on purpose: parity with the reference is 1e-5 and the inputs are exact; a tensor-core
 // version needs a 3-term bf16 split of the weights (pixels are exact in bf16) - noted in DESIGN.md.
 #include "common.cuh"
@@ -31,7 +34,7 @@ constexpr int kC1S = 4;       // stride
 constexpr int kC1Out = 16;    // output channels
 constexpr int kC1Taps = kC1In * kC1K * kC1K;  // 256
 constexpr int kFwdThreads = 128;
-constexpr int kWgradThreads = 256;
+constexpr int kWgradThreads = 64;       // each thread owns 4 filter taps x 16 channels
 constexpr float kInv255 = 1.0f / 255.0f;      // python 1./255 rounded to fp32 (atari_ff_model.py:51)
 
 __device__ __forceinline__ void stage_image(uint8_t* s_img, const uint8_t* __restrict__ src, int bytes,
@@ -134,11 +137,13 @@ conv1_wgrad_kernel(const uint8_t* __restrict__ obs, const int64_t* __restrict__ 
     float* s_g = reinterpret_cast<float*>(smem);                       // [P][16]
     uint8_t* s_img = smem + static_cast<size_t>(P) * kC1Out * sizeof(float);
     const int img_bytes = kC1In * H * W;
-    const int k = threadIdx.x;                                          // filter tap 0..255
-    const int c = k >> 6, ky = (k >> 3) & 7, kx = k & 7;
-    float acc[kC1Out];
+    const int t = threadIdx.x;                                          // taps t + 64*c, c = 0..3
+    const int ky = (t >> 3) & 7, kx = t & 7;
+    float acc[kC1In][kC1Out];
 #pragma unroll
-    for (int oc = 0; oc < kC1Out; ++oc) acc[oc] = 0.0f;
+    for (int c = 0; c < kC1In; ++c)
+#pragma unroll
+        for (int oc = 0; oc < kC1Out; ++oc) acc[c][oc] = 0.0f;
     float accb = 0.0f;                                                  // threads 0..15: bias gradient
 
     for (int n = blockIdx.x; n < N; n += gridDim.x) {
@@ -147,26 +152,36 @@ conv1_wgrad_kernel(const uint8_t* __restrict__ obs, const int64_t* __restrict__ 
         stage_image(s_img, obs + r * img_bytes, img_bytes, threadIdx.x, kWgradThreads);
         const float* yn = Y + static_cast<int64_t>(n) * kC1Out * P;
         const float* gn = dY + static_cast<int64_t>(n) * kC1Out * P;
-        for (int i = threadIdx.x; i < kC1Out * P; i += kWgradThreads) {  // coalesced read, transposed store
-            const int oc = i / P, p = i - oc * P;
-            const float g = gn[i];
-            s_g[p * kC1Out + oc] = (!relu || yn[i] > 0.0f) ? g : 0.0f;   // ReLU backward (threshold)
+        // [oc][p] -> [p][oc]: consecutive threads take consecutive oc of one position so the
+        // transposed store is conflict free (the strided global read is served from L2 sectors)
+        for (int i = threadIdx.x; i < kC1Out * P; i += kWgradThreads) {
+            const int p = i >> 4, oc = i & 15;
+            const int gi = oc * P + p;
+            const float g = gn[gi];
+            s_g[i] = (!relu || yn[gi] > 0.0f) ? g : 0.0f;               // ReLU backward (threshold)
         }
         __syncthreads();
-        const uint8_t* base = s_img + (c * H + ky) * W + kx;
+        const uint8_t* base = s_img + ky * W + kx;
+        const int plane = H * W;
         for (int oy = 0; oy < OH; ++oy) {
             const uint8_t* rowp = base + oy * kC1S * W;
             const float4* gp = reinterpret_cast<const float4*>(s_g + static_cast<size_t>(oy) * OW * kC1Out);
-#pragma unroll 4
+#pragma unroll 2
             for (int ox = 0; ox < OW; ++ox) {
-                const float x = __fmul_rn(static_cast<float>(rowp[ox * kC1S]), kInv255);
+                float x[kC1In];
+#pragma unroll
+                for (int c = 0; c < kC1In; ++c)
+                    x[c] = __fmul_rn(static_cast<float>(rowp[c * plane + ox * kC1S]), kInv255);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 g = gp[ox * 4 + q];
-                    acc[4 * q] = fmaf(x, g.x, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(x, g.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(x, g.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(x, g.w, acc[4 * q + 3]);
+#pragma unroll
+                    for (int c = 0; c < kC1In; ++c) {
+                        acc[c][4 * q] = fmaf(x[c], g.x, acc[c][4 * q]);
+                        acc[c][4 * q + 1] = fmaf(x[c], g.y, acc[c][4 * q + 1]);
+                        acc[c][4 * q + 2] = fmaf(x[c], g.z, acc[c][4 * q + 2]);
+                        acc[c][4 * q + 3] = fmaf(x[c], g.w, acc[c][4 * q + 3]);
+                    }
                 }
             }
         }
@@ -178,7 +193,9 @@ conv1_wgrad_kernel(const uint8_t* __restrict__ obs, const int64_t* __restrict__ 
     }
     float* out = partial + static_cast<int64_t>(blockIdx.x) * (kC1Out * kC1Taps + kC1Out);
 #pragma unroll
-    for (int oc = 0; oc < kC1Out; ++oc) out[oc * kC1Taps + k] = acc[oc];   // [oc][c][ky][kx]
+    for (int c = 0; c < kC1In; ++c)
+#pragma unroll
+        for (int oc = 0; oc < kC1Out; ++oc) out[oc * kC1Taps + c * 64 + t] = acc[c][oc];   // [oc][c][ky][kx]
     if (threadIdx.x < kC1Out) out[kC1Out * kC1Taps + threadIdx.x] = accb;
 }
 
@@ -234,7 +251,7 @@ int rl_conv1_u8_forward(const uint8_t* obs, const int64_t* rows, const float* we
 int64_t rl_conv1_u8_wgrad_scratch_bytes(void) {
     int sms = rl::sm_count();
     if (sms <= 0) sms = 148;
-    return static_cast<int64_t>(sms) * 2 * (rl::kC1Out * rl::kC1Taps + rl::kC1Out) * sizeof(float);
+    return static_cast<int64_t>(sms) * 4 * (rl::kC1Out * rl::kC1Taps + rl::kC1Out) * sizeof(float);
 }
 
 int rl_conv1_u8_wgrad(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
@@ -256,7 +273,7 @@ int rl_conv1_u8_wgrad(const uint8_t* obs, const int64_t* rows, const float* out,
     RL_REQUIRE(smem <= 200 * 1024, RL_EINVAL, "rl_conv1_u8_wgrad: image too large for shared memory");
     int sms = rl::sm_count();
     if (sms <= 0) sms = 148;
-    int64_t grid = static_cast<int64_t>(sms) * 2;
+    int64_t grid = static_cast<int64_t>(sms) * 4;  // 4 CTAs of 2 warps per SM (54 KB smem each)
     if (grid > N) grid = N;
     float* partial = static_cast<float*>(scratch);
     cudaStream_t st = rl::as_stream(stream);

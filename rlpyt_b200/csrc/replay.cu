@@ -61,9 +61,19 @@ replay_extract_kernel(ReplayView v, ReplayOut o, const int64_t* __restrict__ T_i
     if (vec) {
         const int64_t nv = v.hw / 16;
         const uint4 zero = make_uint4(0, 0, 0, 0);
-        for (int64_t j = threadIdx.x; j < nv; j += kExtractThreads) {
-            const uint4 x = blank ? zero : ldg_stream(reinterpret_cast<const uint4*>(src) + j);
-            stg_stream(reinterpret_cast<uint4*>(dst) + j, x);
+        constexpr int kU = 4;  // independent 16 B loads in flight per thread (441 uint4 per 84x84 frame)
+        for (int64_t j0 = threadIdx.x; j0 < nv; j0 += kExtractThreads * kU) {
+            uint4 x[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
+                x[u] = (blank || j >= nv) ? zero : ldg_stream(reinterpret_cast<const uint4*>(src) + j);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
+                if (j < nv) stg_stream(reinterpret_cast<uint4*>(dst) + j, x[u]);
+            }
         }
     } else {
         for (int64_t j = threadIdx.x; j < v.hw; j += kExtractThreads) dst[j] = blank ? uint8_t(0) : src[j];

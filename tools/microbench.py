@@ -100,7 +100,68 @@ def bench_gemm(reps):
             speedup_vs_cublas_fp32=med_t / med)
 
 
-BENCHES = {"returns": bench_returns, "gemm": bench_gemm}
+def make_replay(size, B=256, device_buf=True):
+    from rlpyt_b200.replays.non_sequence.frame import PrioritizedReplayFrameBuffer
+    from rlpyt_b200.utils.collections import namedarraytuple
+    Ex = namedarraytuple("SamplesToBuffer", ["observation", "action", "reward", "done"])
+    ex = Ex(observation=np.zeros((4, 84, 84), np.uint8), action=np.int64(0), reward=np.float32(0), done=np.bool_(False))
+    buf = PrioritizedReplayFrameBuffer(example=ex, size=size, B=B, discount=0.99, n_step_return=3, alpha=0.6, beta=0.4,
+                                       default_priority=1)
+    T = 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.randint(0, 256, (T, B, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    n_app = buf.T // T + 2
+    for i in range(n_app):
+        buf.append_samples(Ex(observation=obs, action=torch.randint(0, 6, (T, B), device="cuda", generator=g),
+                              reward=torch.randn(T, B, device="cuda", generator=g),
+                              done=torch.rand(T, B, device="cuda", generator=g) < 0.005))
+    return buf, Ex
+
+
+def bench_replay(reps):
+    """BASELINE.json config 4: 1M-frame prioritized frame replay, batch 512, n-step 3."""
+    import time
+    buf, Ex = make_replay(1_000_000)
+    np.random.seed(0)
+    pri = torch.rand(512, device="cuda") + 0.01
+    med, best = timeit(lambda: buf.sample_batch(512), reps, flush=True)
+    out(kernel="replay.sample_batch(512)", frames=buf.size, us_med=med * 1e6, us_best=best * 1e6,
+        samples_per_s=512 / med)
+    buf.sample_batch(512)
+    med_u, _ = timeit(lambda: buf.update_batch_priorities(pri), reps, flush=False)
+    out(kernel="replay.update_batch_priorities(512)", us_med=med_u * 1e6)
+    # extraction kernel alone (fixed indices): HBM-bound gather
+    (T_idxs, B_idxs), _p = buf.priority_tree.sample(512)
+    med_e, best_e = timeit(lambda: buf.extract_batch(T_idxs, B_idxs), reps, flush=True)
+    nbytes = 2 * 2 * 512 * 4 * 84 * 84
+    out(kernel="replay_extract_kernel", n=512, us_med=med_e * 1e6, us_best=best_e * 1e6, GBs=nbytes / med_e / 1e9,
+        frac_hbm=nbytes / med_e / 1e9 / HBM, algorithmic_bytes=nbytes)
+    t_adv, _ = timeit(lambda: buf.priority_tree.advance(0) or buf.priority_tree._update_segment(
+        128 * 256, leaf_base=buf.priority_tree.low_idx, scalar=1.0), 5, flush=False)
+    out(kernel="sumtree advance segment (32768 leaves, 20 levels)", us_med=t_adv * 1e6)
+    # CPU oracle (reference algorithm restated) on a smaller ring: per-batch cost is size independent
+    from oracle.replay import FrameReplay
+    o = FrameReplay((4, 84, 84), 100_000, 256, discount=0.99, n_step_return=3)
+    rng = np.random.default_rng(0)
+    obs = rng.integers(0, 256, size=(64, 256, 4, 84, 84), dtype=np.uint8)
+    for i in range(8):
+        o.append_samples(dict(observation=obs, action=rng.integers(0, 6, (64, 256)), reward=rng.standard_normal((64, 256)).astype(np.float32),
+                              done=rng.random((64, 256)) < 0.005))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        o.sample_batch(512)
+    cpu_s = (time.perf_counter() - t0) / 20
+    new = np.abs(rng.standard_normal(512)).astype(np.float32)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        o.sample_batch(512)
+        o.update_batch_priorities(new)
+    cpu_su = (time.perf_counter() - t0) / 20 - cpu_s
+    out(kernel="oracle(CPU) replay.sample_batch(512)", ms=cpu_s * 1e3, update_ms=cpu_su * 1e3,
+        speedup_sample=cpu_s / med, speedup_update=cpu_su / med_u)
+
+
+BENCHES = {"returns": bench_returns, "gemm": bench_gemm, "replay": bench_replay}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -70,5 +70,21 @@ def gae():
         torch.cuda.profiler.stop()
 
 
+def replay():
+    from tools.microbench import make_replay
+    buf, Ex = make_replay(200_000)
+    np.random.seed(0)
+    pri = torch.rand(512, device="cuda") + 0.01
+    buf.sample_batch(512)
+    buf.update_batch_priorities(pri)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    buf.sample_batch(512)
+    buf.update_batch_priorities(pri)
+    buf.priority_tree.advance(128)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 if __name__ == "__main__":
-    {"ppo": ppo, "gae": gae}[sys.argv[1]]()
+    {"ppo": ppo, "gae": gae, "replay": replay}[sys.argv[1]]()
