@@ -199,8 +199,12 @@ int rl_conv1_u8_wgrad(const uint8_t* obs, const int64_t* rows, const float* out,
  * dgrad / wgrad (with transposed operands).  tcgen05.mma kind::tf32 with a 3-term hi/lo split
  * (fp32-level accuracy), TMA-staged, accumulators in TMEM.  All row-major fp32, K %% 4 == 0,
  * 16-byte aligned bases; bias nullable. */
+/* workspace: rl_gemm_tf32x3_workspace_bytes(M,N,K) bytes (0 = none needed; nullable): when the
+ * tile grid cannot fill the SMs (agent.step: M = 256) K is split over up to 16 CTAs per tile and
+ * the partial tiles are summed in order by a second kernel. */
+int64_t rl_gemm_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N,
-                       int64_t K, int relu, void* stream);
+                       int64_t K, int relu, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

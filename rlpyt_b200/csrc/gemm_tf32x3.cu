@@ -130,7 +130,8 @@ __device__ __forceinline__ void split4(float4& v, float4& lo) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu) {
+                   float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu,
+                   int kb_per_split) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -143,7 +144,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb = (K + BK - 1) / BK;
+    // split-K (small M): blockIdx.z owns k-blocks [kb0, kb0 + num_kb) and writes its partial tile to
+    // slice z of the workspace C[z][M][N]; splitk_reduce_kernel sums the slices in order.
+    const int total_kb = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int num_kb = min(kb_per_split, total_kb - kb0);
+    C += static_cast<int64_t>(blockIdx.z) * M * N;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -178,8 +184,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * kStageBytes;
                 mbar_expect_tx(&full_tma[s], 2 * kTileBytes);
-                tma_load_2d(st, &map_a, kb * BK, m0, &full_tma[s]);
-                tma_load_2d(st + 2 * kTileBytes, &map_b, kb * BK, n0, &full_tma[s]);
+                tma_load_2d(st, &map_a, (kb0 + kb) * BK, m0, &full_tma[s]);
+                tma_load_2d(st + 2 * kTileBytes, &map_b, (kb0 + kb) * BK, n0, &full_tma[s]);
             }
         }
     } else if (warp == 1) {
@@ -288,6 +294,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
+// out[m][n] = sum_z ws[z][m][n] (+ bias[n]) (+ ReLU), z in ascending order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ out, int64_t MN, int N, int relu) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= MN) return;
+    float s = 0.0f;
+    for (int z = 0; z < splits; ++z) s += ws[static_cast<int64_t>(z) * MN + i];
+    if (bias != nullptr) s += bias[i % N];
+    out[i] = relu ? fmaxf(s, 0.0f) : s;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -324,8 +341,23 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K
 
 extern "C" {
 
+int64_t rl_gemm_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ((M + rl::gemm::BM - 1) / rl::gemm::BM) * ((N + rl::gemm::BN - 1) / rl::gemm::BN);
+    const int64_t kb = (K + rl::gemm::BK - 1) / rl::gemm::BK;
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    int64_t splits = 1;
+    if (tiles * 2 <= sms) {                       // fewer than half a wave of tiles: split K
+        splits = sms / tiles;
+        if (splits > kb / 4) splits = kb / 4;     // keep >= 4 k-blocks (one promotion chunk) per split
+        if (splits > 16) splits = 16;
+        if (splits < 1) splits = 1;
+    }
+    return splits > 1 ? splits * M * N * static_cast<int64_t>(sizeof(float)) : 0;
+}
+
 int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N,
-                       int64_t K, int relu, void* stream) {
+                       int64_t K, int relu, void* workspace, void* stream) {
     RL_REQUIRE(A && B && C, RL_EINVAL, "rl_gemm_tf32x3_f32: null pointer");
     RL_REQUIRE(M >= 1 && N >= 1 && K >= 1, RL_EINVAL, "rl_gemm_tf32x3_f32: M=%lld N=%lld K=%lld", (long long)M,
                (long long)N, (long long)K);
@@ -342,11 +374,30 @@ int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float*
                              rl::gemm::kSmemBytes);
         attr_set = true;
     }
+    const int64_t ws_bytes = rl_gemm_tf32x3_workspace_bytes(M, N, K);
+    const int total_kb = static_cast<int>((K + rl::gemm::BK - 1) / rl::gemm::BK);
+    int splits = static_cast<int>(ws_bytes / (M * N * static_cast<int64_t>(sizeof(float))));
+    if (splits < 1 || workspace == nullptr) splits = 1;
+    int kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per_split - 1) / kb_per_split;   // no empty split
+    cudaStream_t st = rl::as_stream(stream);
     dim3 grid(static_cast<unsigned>((N + rl::gemm::BN - 1) / rl::gemm::BN),
-              static_cast<unsigned>((M + rl::gemm::BM - 1) / rl::gemm::BM));
-    rl::gemm::gemm_tf32x3_kernel<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, rl::as_stream(stream)>>>(
-        ma, mb, C, bias, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), relu);
-    return rl::check_launch("gemm_tf32x3_kernel");
+              static_cast<unsigned>((M + rl::gemm::BM - 1) / rl::gemm::BM), static_cast<unsigned>(splits));
+    if (splits == 1) {
+        rl::gemm::gemm_tf32x3_kernel<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
+            ma, mb, C, bias, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), relu, total_kb);
+        return rl::check_launch("gemm_tf32x3_kernel");
+    }
+    RL_REQUIRE(rl::aligned(workspace, 16), RL_EALIGN, "rl_gemm_tf32x3_f32: workspace must be 16B aligned");
+    float* ws = static_cast<float*>(workspace);
+    rl::gemm::gemm_tf32x3_kernel<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
+        ma, mb, ws, nullptr, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), 0, kb_per_split);
+    rc = rl::check_launch("gemm_tf32x3_kernel");
+    if (rc != RL_OK) return rc;
+    const int64_t MN = M * N;
+    rl::gemm::splitk_reduce_kernel<<<static_cast<unsigned>((MN + 255) / 256), 256, 0, st>>>(
+        ws, splits, bias, C, MN, static_cast<int>(N), relu);
+    return rl::check_launch("splitk_reduce_kernel");
 }
 
 }  // extern "C"

@@ -6,6 +6,8 @@ import torch
 
 from rlpyt_b200 import _lib
 
+_WS = {}  # split-K workspaces, keyed by (device, bytes)
+
 
 def gemm_tn(a, b, bias=None, relu=False):
     """a [M,K] @ b[N,K]^T (+bias) (+relu) -> [M,N]; fp32 CUDA, K % 4 == 0."""
@@ -15,9 +17,17 @@ def gemm_tn(a, b, bias=None, relu=False):
     N = b.shape[0]
     assert b.shape[1] == K and a.dtype == torch.float32 and b.dtype == torch.float32
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ws_bytes = int(_lib.load().rl_gemm_tf32x3_workspace_bytes(M, N, K))
+    ws = None
+    if ws_bytes:
+        key = (str(a.device), ws_bytes)
+        ws = _WS.get(key)
+        if ws is None:
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
+            _WS[key] = ws
     with torch.cuda.device(a.device):
         _lib.call("rl_gemm_tf32x3_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), M, N, K,
-                  int(bool(relu)), _lib.stream())
+                  int(bool(relu)), _lib.ptr(ws), _lib.stream(), n_launch=2 if ws is not None else 1)
     return out
 
 

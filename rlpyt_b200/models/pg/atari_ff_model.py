@@ -45,9 +45,9 @@ class AtariFfModel(torch.nn.Module):
         v = self.value(fc_out).squeeze(-1)
         return pi.view(lead_shape + pi.shape[1:]), v.view(lead_shape)
 
-    # below this many rows the 128x128-tile tensor-core GEMM cannot fill the 148 SMs and cuBLAS'
-    # fp32 kernel is faster (measured: M=256 107 us vs 65 us; M=8192 203 us vs 486 us)
-    TC_GEMM_MIN_ROWS = 2048
+    # tiny batches (the single example step at start-up) stay on cuBLAS; from B=64 up the tcgen05 GEMM
+    # is used - with split-K when the 128x128 tile grid cannot fill the 148 SMs (agent.step, M=256)
+    TC_GEMM_MIN_ROWS = 64
 
     def _head(self, flat):
         """Linear(conv_out -> fc) + ReLU: the fp32-accurate tcgen05 GEMM for minibatch-sized inputs."""
