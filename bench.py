@@ -327,8 +327,24 @@ def cpu_baseline(U):
         gpu_unit()
     torch.cuda.synchronize()
     gpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    # the same 1 + 16 x 4 launches captured once and replayed as a CUDA graph (how a deployment would
+    # issue a fixed-shape unit): wall time == device time, no per-call Python / ctypes cost
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gpu_unit()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    graph_ms = e0.elapsed_time(e1) / 50
     unit = {"what": "GAE [128,256] + 16 x PPO-loss fwd+bwd (N=8192, A=6), no network", "cpu_ms": cpu_ms,
-            "gpu_ms_wall_incl_python": gpu_ms, "speedup": cpu_ms / gpu_ms, "cpu_threads": threads}
+            "gpu_ms_cuda_graph": graph_ms, "speedup": cpu_ms / graph_ms,
+            "gpu_ms_eager_wall_incl_python": gpu_ms, "speedup_eager": cpu_ms / gpu_ms, "cpu_threads": threads}
     return base, unit
 
 
