@@ -206,6 +206,17 @@ int64_t rl_gemm_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N,
                        int64_t K, int relu, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------ conv layers as tcgen05 implicit GEMM
+ * Same contracts as rl_conv1_u8_forward (uint8 frames, optional row gather, *1/255, k8 s4, 4->16)
+ * and as Conv2d(16->32, k4, s2, p1)(+bias)(+ReLU) on fp32 NCHW activations
+ * (rlpyt/models/conv2d.py:36-44, rlpyt/models/pg/atari_ff_model.py:31-35, :50-53), computed on the
+ * tensor cores: tcgen05.mma kind::tf32 with the fp32-accurate hi/lo operand split, im2col gathered on
+ * the fly into the swizzled shared-memory operand tiles, accumulators in TMEM. */
+int rl_conv1_u8_forward_tc(const uint8_t* obs, const int64_t* rows, const float* weight, const float* bias,
+                           float* out, int64_t N, int C, int H, int W, int relu, void* stream);
+int rl_conv2_forward_tc(const float* x, const float* weight, const float* bias, float* out, int64_t N,
+                        int C, int IH, int IW, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

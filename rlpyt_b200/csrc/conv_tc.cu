@@ -1,0 +1,300 @@
+// Convolution forward as an IMPLICIT GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32 with the
+// fp32-accurate hi/lo split of gemm_tf32x3.cu) for the two conv layers of the AtariFf network.
+//
+// Reference: rlpyt/models/conv2d.py:36-44 with the defaults of rlpyt/models/pg/atari_ff_model.py:31-35:
+//   layer 1: uint8 frames [N,4,H,W] -> *1/255 -> Conv2d(4->16, k8, s4, p0) + ReLU
+//   layer 2: fp32 [N,16,IH,IW]      ->           Conv2d(16->32, k4, s2, p1) + ReLU
+// Both are GEMMs with K = C*KH*KW = 256:  Y[m, oc] = sum_k A[m, k] * W[oc, k], one row m per output
+// position (n, oy, ox), A = im2col(X) never materialised.
+//
+//   * A producer (4 warps, thread = one output position of the 128-row tile): for each 32-wide
+//     k-block it gathers 8 chunks of 4 consecutive taps (4 pixels of one filter row; coalesced across
+//     the warp because neighbouring lanes are neighbouring positions), splits them into TF32 hi/lo
+//     and writes them straight into the K-major SWIZZLE_128B layout the MMA expects
+//     (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)) in a 3-stage ring; layer 1 keeps the pixels as
+//     the integers 0..255 - exact in TF32, so A needs no lo term - and applies 1/255 in the epilogue.
+//   * B (the filter bank, [oc][256] = the weight tensor as stored) is split and swizzled into shared
+//     memory once per persistent CTA.
+//   * MMA warp: per k-block 4 x (2|3) tcgen05.mma (M=128, N=16|32, K=8); the two halves of K go to
+//     separate TMEM accumulators that the epilogue adds in fp32 (halves the accumulator truncation),
+//     and the accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * epilogue (4 warps): tcgen05.ld -> (+bias, *scale, ReLU) -> NCHW stores, coalesced over positions.
+// cuDNN's fp32 kernels: 0.86 ms (layer 2) per 8192-sample minibatch; the fp32 SIMT kernel of conv1.cu:
+// 0.80 ms (layer 1).
+#include "tc_common.cuh"
+
+namespace rl {
+namespace convtc {
+
+using namespace tc;
+
+constexpr int kRows = 128;                 // GEMM M tile = output positions per tile
+constexpr int kK = 256;                    // C*KH*KW for both layers
+constexpr int kKB = kK / 32;               // 8 k-blocks of 32
+constexpr int kStages = 3;
+constexpr int kTileBytes = kRows * 128;    // 16 KiB: 128 rows x 128 B
+constexpr int kProducerThreads = 128, kEpilogueThreads = 128;
+constexpr int kThreads = 288;              // warps 0-3 producers, 4-7 epilogue, 8 MMA + TMEM alloc
+constexpr int kTmemCols = 128;
+
+struct Geom {
+    int n_img, C, H, W, OH, OW, P;         // P = OH*OW
+    int64_t m_total;                       // n_img * P
+};
+
+// ---- layer policies -------------------------------------------------------------------------------
+struct Layer2 {                            // fp32 input, k4 s2 p1, 16 -> 32
+    static constexpr int kN = 32, kTerms = 3, KH = 4, KW = 4, S = 2, PAD = 1;
+    using In = float;
+    __device__ static float4 gather(const float* __restrict__ xn, const Geom& g, int oy, int ox, int kb, int j) {
+        const int c = kb * 2 + (j >> 2), ky = j & 3;
+        const int iy = oy * S + ky - PAD, ix0 = ox * S - PAD;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < g.H) {
+            const float* row = xn + (c * g.H + iy) * g.W;
+            if (ix0 >= 0) v.x = row[ix0];
+            v.y = row[ix0 + 1];
+            if (ix0 + 2 < g.W) v.z = row[ix0 + 2];
+            if (ix0 + 3 < g.W) v.w = row[ix0 + 3];
+        }
+        return v;
+    }
+    static constexpr float kScale = 1.0f;
+};
+
+struct Layer1 {                            // uint8 input, k8 s4 p0, 4 -> 16; pixels stay integers
+    static constexpr int kN = 16, kTerms = 2, KH = 8, KW = 8, S = 4, PAD = 0;
+    using In = uint8_t;
+    __device__ static float4 gather(const uint8_t* __restrict__ xn, const Geom& g, int oy, int ox, int kb, int j) {
+        const int k0 = kb * 32 + j * 4;
+        const int c = k0 >> 6, ky = (k0 >> 3) & 7, kx0 = k0 & 7;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(xn + (c * g.H + oy * S + ky) * g.W + ox * S + kx0);
+        return make_float4(static_cast<float>(v & 0xffu), static_cast<float>((v >> 8) & 0xffu),
+                           static_cast<float>((v >> 16) & 0xffu), static_cast<float>(v >> 24));
+    }
+    static constexpr float kScale = 1.0f / 255.0f;
+};
+
+template <class L>
+struct Smem {
+    static constexpr int kBBytes = kKB * L::kN * 128;                 // one term of B, all k-blocks
+    static constexpr int kATerms = (L::kTerms == 3) ? 2 : 1;          // A hi (+ lo)
+    static constexpr int kStageBytes = kATerms * kTileBytes;
+    static constexpr int kTotal = 2 * kBBytes + kStages * kStageBytes + 1024 + 256;
+};
+
+template <class L>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restrict__ rows,
+                   const float* __restrict__ Wg, const float* __restrict__ bias, float* __restrict__ Y,
+                   Geom g, int relu) {
+    using S = Smem<L>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = smem + S::kBBytes;
+    uint8_t* a_ring = smem + 2 * S::kBBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + kStages * S::kStageBytes);
+    uint64_t* a_full = bars;                   // [kStages] producers -> MMA
+    uint64_t* a_empty = bars + kStages;        // [kStages] MMA -> producers
+    uint64_t* acc_full = bars + 2 * kStages;   // [2] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t num_tiles = (g.m_total + kRows - 1) / kRows;
+    constexpr uint32_t kIdesc = make_idesc_tf32(kRows, L::kN);
+
+    // ---- one-time setup: barriers, TMEM, filter bank -> swizzled hi/lo tiles
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&a_full[s], kProducerThreads);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], kEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = threadIdx.x; i < L::kN * (kK / 4); i += kThreads) {   // one 16-byte chunk each
+        const int oc = i / (kK / 4), ch = i % (kK / 4);                // ch = global chunk index (k = 4*ch)
+        const int kb = ch >> 3, j = ch & 7;
+        const float4 w = *reinterpret_cast<const float4*>(Wg + oc * kK + ch * 4);
+        float4 hi, lo;
+        split_tf32(w.x, hi.x, lo.x); split_tf32(w.y, hi.y, lo.y);
+        split_tf32(w.z, hi.z, lo.z); split_tf32(w.w, hi.w, lo.w);
+        const int off = kb * L::kN * 128 + oc * 128 + ((j ^ (oc & 7)) << 4);
+        *reinterpret_cast<float4*>(b_hi + off) = hi;
+        *reinterpret_cast<float4*>(b_lo + off) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ================================================================ A producers
+        const int r = threadIdx.x;
+        const int swz = r & 7;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int64_t m = tile * kRows + r;
+            const bool valid = m < g.m_total;
+            const int64_t n = valid ? m / g.P : 0;
+            const int pos = valid ? static_cast<int>(m - n * g.P) : 0;
+            const int oy = pos / g.OW, ox = pos - oy * g.OW;
+            const int64_t img = rows != nullptr ? rows[n] : n;
+            const typename L::In* xn = X + img * (static_cast<int64_t>(g.C) * g.H * g.W);
+            for (int kb = 0; kb < kKB; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(&a_empty[s], ph ^ 1);
+                uint8_t* st = a_ring + s * S::kStageBytes + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = valid ? L::gather(xn, g, oy, ox, kb, j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int off = (j ^ swz) << 4;
+                    if (L::kTerms == 3) {
+                        float4 hi, lo;
+                        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+                        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                        *reinterpret_cast<float4*>(st + off) = hi;
+                        *reinterpret_cast<float4*>(st + kTileBytes + off) = lo;
+                    } else {
+                        *reinterpret_cast<float4*>(st + off) = v;   // integers 0..255: exact in TF32
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&a_full[s]);
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================================ MMA issuer
+        uint32_t it = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int buf = tcount & 1;
+            mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < kKB; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(&a_full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const int half = kb / (kKB / 2);
+                    const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 2 * L::kN + half * L::kN);
+                    const uint8_t* st = a_ring + s * S::kStageBytes;
+                    const uint64_t da_hi = make_desc(st), da_lo = make_desc(st + kTileBytes);
+                    const uint64_t db_hi = make_desc(b_hi + kb * L::kN * 128), db_lo = make_desc(b_lo + kb * L::kN * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = static_cast<uint64_t>(k * 2);
+                        umma_tf32(acc, da_hi + adv, db_hi + adv, kIdesc, ((kb % (kKB / 2)) > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(acc, da_hi + adv, db_lo + adv, kIdesc, 1u);
+                        if (L::kTerms == 3) umma_tf32(acc, da_lo + adv, db_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(&a_empty[s]);
+                    if (kb == kKB - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================ epilogue (warps 4..7)
+        const int q = warp - 4;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int buf = tcount & 1;
+            mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r0[32], r1[32];
+            const uint32_t col = static_cast<uint32_t>(buf * 2 * L::kN);
+            if (L::kN == 32) {
+                tmem_ld32(tmem_base + lane_base + col, r0);
+                tmem_ld32(tmem_base + lane_base + col + 32, r1);
+            } else {
+                tmem_ld32(tmem_base + lane_base + col, r0);       // 2 x 16 columns: both halves in one load
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[buf]);
+            const int64_t m = tile * kRows + r;
+            if (m < g.m_total) {
+                const int64_t n = m / g.P;
+                const int pos = static_cast<int>(m - n * g.P);
+                float* yb = Y + n * (static_cast<int64_t>(L::kN) * g.P) + pos;
+#pragma unroll
+                for (int oc = 0; oc < L::kN; ++oc) {
+                    const float a = (L::kN == 32) ? __uint_as_float(r0[oc]) + __uint_as_float(r1[oc])
+                                                  : __uint_as_float(r0[oc]) + __uint_as_float(r0[16 + oc]);
+                    float v = a * L::kScale + bias[oc];
+                    if (relu) v = fmaxf(v, 0.0f);
+                    yb[static_cast<int64_t>(oc) * g.P] = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+template <class L>
+static int launch(const typename L::In* X, const int64_t* rows, const float* W, const float* bias, float* Y,
+                  Geom g, int relu, cudaStream_t st) {
+    using S = Smem<L>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_fwd_tc_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        attr_set = true;
+    }
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int64_t num_tiles = (g.m_total + kRows - 1) / kRows;
+    const int64_t grid = num_tiles < sms ? num_tiles : sms;
+    conv_fwd_tc_kernel<L><<<static_cast<unsigned>(grid), kThreads, S::kTotal, st>>>(X, rows, W, bias, Y, g, relu);
+    return check_launch("conv_fwd_tc_kernel");
+}
+
+}  // namespace convtc
+}  // namespace rl
+
+extern "C" {
+
+int rl_conv1_u8_forward_tc(const uint8_t* obs, const int64_t* rows, const float* weight, const float* bias,
+                           float* out, int64_t N, int C, int H, int W, int relu, void* stream) {
+    RL_REQUIRE(obs && weight && bias && out, RL_EINVAL, "rl_conv1_u8_forward_tc: null pointer");
+    RL_REQUIRE(N >= 0 && C == 4 && H >= 8 && W >= 8 && W % 4 == 0, RL_EINVAL,
+               "rl_conv1_u8_forward_tc: needs C=4, W %% 4 == 0 (got C=%d H=%d W=%d)", C, H, W);
+    RL_REQUIRE(rl::aligned(obs, 4) && rl::aligned(weight, 16), RL_EALIGN, "rl_conv1_u8_forward_tc: alignment");
+    if (N == 0) return RL_OK;
+    rl::convtc::Geom g;
+    g.n_img = static_cast<int>(N); g.C = C; g.H = H; g.W = W;
+    g.OH = (H - 8) / 4 + 1; g.OW = (W - 8) / 4 + 1; g.P = g.OH * g.OW; g.m_total = N * g.P;
+    return rl::convtc::launch<rl::convtc::Layer1>(obs, rows, weight, bias, out, g, relu, rl::as_stream(stream));
+}
+
+int rl_conv2_forward_tc(const float* x, const float* weight, const float* bias, float* out, int64_t N,
+                        int C, int IH, int IW, int relu, void* stream) {
+    RL_REQUIRE(x && weight && bias && out, RL_EINVAL, "rl_conv2_forward_tc: null pointer");
+    RL_REQUIRE(N >= 0 && C == 16 && IH >= 2 && IW >= 2, RL_EINVAL, "rl_conv2_forward_tc: needs C=16 (got C=%d %dx%d)",
+               C, IH, IW);
+    RL_REQUIRE(rl::aligned(weight, 16), RL_EALIGN, "rl_conv2_forward_tc: weight must be 16B aligned");
+    if (N == 0) return RL_OK;
+    rl::convtc::Geom g;
+    g.n_img = static_cast<int>(N); g.C = C; g.H = IH; g.W = IW;
+    g.OH = (IH + 2 - 4) / 2 + 1; g.OW = (IW + 2 - 4) / 2 + 1; g.P = g.OH * g.OW; g.m_total = N * g.P;
+    return rl::convtc::launch<rl::convtc::Layer2>(x, nullptr, weight, bias, out, g, relu, rl::as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,11 +1,15 @@
 """``Conv2d(4->16, k8, s4) + ReLU`` on uint8 frames as one autograd op over the hand-written kernels
 of csrc/conv1.cu (forward fused with the row gather and the ``/255`` scaling; backward = weight and
 bias gradients - the input is an observation and needs none)."""
+import os
+
 import torch
 
 from rlpyt_b200 import _lib
 
 _SCRATCH = {}
+# forward implementation: "tc" = tcgen05 implicit GEMM (csrc/conv_tc.cu), "simt" = fp32 kernel (csrc/conv1.cu)
+FORWARD_IMPL = os.environ.get("RLPYT_B200_CONV1_FWD", "tc")
 
 
 def supported(image_shape, conv_layers):
@@ -31,7 +35,7 @@ class Conv1U8Relu(torch.autograd.Function):
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
         out = torch.empty((N, 16, OH, OW), dtype=torch.float32, device=obs.device)
         with torch.cuda.device(obs.device):
-            _lib.call("rl_conv1_u8_forward", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
+            _lib.call("rl_conv1_u8_forward_tc" if FORWARD_IMPL == "tc" else "rl_conv1_u8_forward", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
                       N, C, H, W, 1, _lib.stream())
         ctx.obs, ctx.rows = obs, rows
         ctx.save_for_backward(out)

@@ -8,7 +8,7 @@ are converted with ``float(x) * (1/255)`` - one fp32 rounding, exactly the refer
 import torch
 import torch.nn.functional as F
 
-from rlpyt_b200.models import conv1_op, gemm_op
+from rlpyt_b200.models import conv1_op, conv2_op, gemm_op
 from rlpyt_b200.models.conv2d import Conv2dHeadModel
 from rlpyt_b200.utils.gather import LazyRows
 from rlpyt_b200.utils.tensor import infer_leading_dims, restore_leading_dims
@@ -33,13 +33,18 @@ class AtariFfModel(torch.nn.Module):
         self.value = torch.nn.Linear(self.conv.output_size, 1)
         # uint8 CUDA frames take the hand-written first layer (csrc/conv1.cu) when the layer is the
         # reference default; anything else goes through the generic torch path below.
-        self.fused_first_layer = conv1_op.supported(self.image_shape, list(self.conv.conv.conv))
+        layers = list(self.conv.conv.conv)
+        self.fused_first_layer = conv1_op.supported(self.image_shape, layers)
+        self.tc_second_layer = len(layers) == 4 and conv2_op.supported(layers[2], layers[3])
         self.accepts_lazy_rows = True
 
     def _fused_forward(self, obs, rows, lead_shape):
         layers = self.conv.conv.conv
         x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, obs, rows)
-        x = layers[2:](x)
+        if self.tc_second_layer:
+            x = conv2_op.conv2_relu(x, layers[2].weight, layers[2].bias)
+        else:
+            x = layers[2:](x)
         fc_out = self._head(x.view(x.shape[0], -1))
         pi = F.softmax(self.pi(fc_out), dim=-1)
         v = self.value(fc_out).squeeze(-1)

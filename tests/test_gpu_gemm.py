@@ -52,3 +52,56 @@ def test_linear_autograd_matches_torch_fp32():
     for got, want in ((x1.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
         s = float(want.abs().max())
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=2e-5 * s)
+
+
+@pytest.mark.parametrize("N,plane", [(1, (20, 20)), (5, (20, 20)), (64, (20, 20)), (300, (25, 19)), (3, (8, 8)), (2, (7, 5))])
+def test_conv2_forward_tcgen05_vs_torch(N, plane):
+    """tcgen05 implicit-GEMM Conv2d(16->32,k4,s2,p1)+ReLU vs torch fp32 (1e-5 of the row scale)."""
+    import torch.nn.functional as F
+    from rlpyt_b200.models.conv2_op import conv2_relu
+    g = torch.Generator(device="cuda").manual_seed(N)
+    x = torch.relu(torch.randn((N, 16) + plane, device="cuda", generator=g))
+    w = torch.randn(32, 16, 4, 4, device="cuda", generator=g) / 16
+    b = torch.randn(32, device="cuda", generator=g) / 4
+    y = conv2_relu(x, w, b)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1))
+    assert y.shape == ref.shape
+    scale = float(F.conv2d(x.double().abs(), w.double().abs(), None, stride=2, padding=1).max())
+    assert float((y.double() - ref).abs().max()) <= 3e-6 * scale
+    x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    x2, w2, b2 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    go = torch.randn(y.shape, device="cuda", generator=g)
+    y1 = conv2_relu(x1, w1, b1)
+    y1.backward(go)
+    pre = F.conv2d(x2, w2, b2, stride=2, padding=1)
+    pre.backward(go * (y1.detach() > 0))
+    for got, want in ((x1.grad, x2.grad), (w1.grad, w2.grad), (b1.grad, b2.grad)):
+        s = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=2e-5 * s)
+
+
+@pytest.mark.parametrize("shape", [(4, 84, 84), (4, 36, 36), (4, 104, 80)])
+@pytest.mark.parametrize("use_rows", [False, True])
+def test_conv1_forward_tcgen05_vs_simt(shape, use_rows):
+    """The tensor-core first layer (integer pixels exact in TF32, weights split hi/lo, 1/255 in the
+    epilogue) against the fp32 SIMT kernel and an fp64 reference."""
+    import torch.nn.functional as F
+    from rlpyt_b200.models import conv1_op
+    g = torch.Generator(device="cuda").manual_seed(9)
+    obs = torch.randint(0, 256, (257,) + shape, dtype=torch.uint8, device="cuda", generator=g)
+    rows = torch.randint(0, 257, (130,), device="cuda", generator=g) if use_rows else None
+    w = (torch.rand(16, 4, 8, 8, device="cuda", generator=g) - 0.5) / 8
+    b = (torch.rand(16, device="cuda", generator=g) - 0.5) / 8
+    old = conv1_op.FORWARD_IMPL
+    try:
+        conv1_op.FORWARD_IMPL = "tc"
+        y_tc = conv1_op.conv1_u8_relu(w, b, obs, rows)
+        conv1_op.FORWARD_IMPL = "simt"
+        y_simt = conv1_op.conv1_u8_relu(w, b, obs, rows)
+    finally:
+        conv1_op.FORWARD_IMPL = old
+    x = (obs if rows is None else obs[rows]).double() / 255
+    ref = F.relu(F.conv2d(x, w.double(), b.double(), stride=4))
+    scale = float(F.conv2d(x.abs(), w.double().abs(), None, stride=4).max())
+    assert float((y_tc.double() - ref).abs().max()) <= 3e-6 * scale
+    np.testing.assert_allclose(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=1e-5, atol=2e-6)
