@@ -7,11 +7,14 @@
 // Both are GEMMs with K = C*KH*KW = 256:  Y[m, oc] = sum_k A[m, k] * W[oc, k], one row m per output
 // position (n, oy, ox), A = im2col(X) never materialised.
 //
-//   * A producer (4 warps, thread = one output position of the 128-row tile): for each 32-wide
-//     k-block it gathers 8 chunks of 4 consecutive taps (4 pixels of one filter row; coalesced across
+//   * A producer (8 warps, two threads per output position of the 128-row tile, each owning 4 of the 8
+//     chunks; the gathers of k-block i+1 are issued before k-block i is written, so two round trips
+//     to L2/HBM are always in flight - the first version, one thread per row without prefetch, spent
+//     90 % of its issue slots stalled on the scoreboard, profiles/r01_conv_tc_first.txt): for each
+//     32-wide k-block it gathers chunks of 4 consecutive taps (4 pixels of one filter row; coalesced across
 //     the warp because neighbouring lanes are neighbouring positions), splits them into TF32 hi/lo
 //     and writes them straight into the K-major SWIZZLE_128B layout the MMA expects
-//     (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)) in a 3-stage ring; layer 1 keeps the pixels as
+//     (chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)) in a 4- / 8-stage ring; layer 1 keeps the pixels as
 //     the integers 0..255 - exact in TF32, so A needs no lo term - and applies 1/255 in the epilogue.
 //   * B (the filter bank, [oc][256] = the weight tensor as stored) is split and swizzled into shared
 //     memory once per persistent CTA.
@@ -31,10 +34,10 @@ using namespace tc;
 constexpr int kRows = 128;                 // GEMM M tile = output positions per tile
 constexpr int kK = 256;                    // C*KH*KW for both layers
 constexpr int kKB = kK / 32;               // 8 k-blocks of 32
-constexpr int kStages = 3;
 constexpr int kTileBytes = kRows * 128;    // 16 KiB: 128 rows x 128 B
-constexpr int kProducerThreads = 128, kEpilogueThreads = 128;
-constexpr int kThreads = 288;              // warps 0-3 producers, 4-7 epilogue, 8 MMA + TMEM alloc
+constexpr int kProducerThreads = 256, kEpilogueThreads = 128;
+constexpr int kThreads = 416;              // warps 0-7 producers, 8-11 epilogue, 12 MMA + TMEM alloc
+constexpr int kMmaWarp = 12, kEpiWarp0 = 8;
 constexpr int kTmemCols = 128;
 
 struct Geom {
@@ -45,7 +48,11 @@ struct Geom {
 // ---- layer policies -------------------------------------------------------------------------------
 struct Layer2 {                            // fp32 input, k4 s2 p1, 16 -> 32
     static constexpr int kN = 32, kTerms = 3, KH = 4, KW = 4, S = 2, PAD = 1;
+    static constexpr int kStages = 4;      // 4 x 32 KiB (hi + lo) + 64 KiB filter bank
     using In = float;
+    using Raw = float4;
+    __device__ static float4 expand(const float4& v) { return v; }
+    __device__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ static float4 gather(const float* __restrict__ xn, const Geom& g, int oy, int ox, int kb, int j) {
         const int c = kb * 2 + (j >> 2), ky = j & 3;
         const int iy = oy * S + ky - PAD, ix0 = ox * S - PAD;
@@ -64,13 +71,19 @@ struct Layer2 {                            // fp32 input, k4 s2 p1, 16 -> 32
 
 struct Layer1 {                            // uint8 input, k8 s4 p0, 4 -> 16; pixels stay integers
     static constexpr int kN = 16, kTerms = 2, KH = 8, KW = 8, S = 4, PAD = 0;
+    static constexpr int kStages = 8;      // 8 x 16 KiB (hi only) + 32 KiB filter bank
     using In = uint8_t;
-    __device__ static float4 gather(const uint8_t* __restrict__ xn, const Geom& g, int oy, int ox, int kb, int j) {
-        const int k0 = kb * 32 + j * 4;
-        const int c = k0 >> 6, ky = (k0 >> 3) & 7, kx0 = k0 & 7;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(xn + (c * g.H + oy * S + ky) * g.W + ox * S + kx0);
+    using Raw = uint32_t;                  // 4 packed pixels; converted only when written to smem so the
+                                           // load stays in flight across the previous stage's stores
+    __device__ static uint32_t zero() { return 0u; }
+    __device__ static float4 expand(uint32_t v) {
         return make_float4(static_cast<float>(v & 0xffu), static_cast<float>((v >> 8) & 0xffu),
                            static_cast<float>((v >> 16) & 0xffu), static_cast<float>(v >> 24));
+    }
+    __device__ static uint32_t gather(const uint8_t* __restrict__ xn, const Geom& g, int oy, int ox, int kb, int j) {
+        const int k0 = kb * 32 + j * 4;
+        const int c = k0 >> 6, ky = (k0 >> 3) & 7, kx0 = k0 & 7;
+        return *reinterpret_cast<const uint32_t*>(xn + (c * g.H + oy * S + ky) * g.W + ox * S + kx0);
     }
     static constexpr float kScale = 1.0f / 255.0f;
 };
@@ -80,7 +93,7 @@ struct Smem {
     static constexpr int kBBytes = kKB * L::kN * 128;                 // one term of B, all k-blocks
     static constexpr int kATerms = (L::kTerms == 3) ? 2 : 1;          // A hi (+ lo)
     static constexpr int kStageBytes = kATerms * kTileBytes;
-    static constexpr int kTotal = 2 * kBBytes + kStages * kStageBytes + 1024 + 256;
+    static constexpr int kTotal = 2 * kBBytes + L::kStages * kStageBytes + 1024 + 256;
 };
 
 template <class L>
@@ -94,6 +107,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + S::kBBytes;
     uint8_t* a_ring = smem + 2 * S::kBBytes;
+    constexpr int kStages = L::kStages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + kStages * S::kStageBytes);
     uint64_t* a_full = bars;                   // [kStages] producers -> MMA
     uint64_t* a_empty = bars + kStages;        // [kStages] MMA -> producers
@@ -108,16 +122,16 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     // ---- one-time setup: barriers, TMEM, filter bank -> swizzled hi/lo tiles
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&a_full[s], kProducerThreads);
+            mbar_init(&a_full[s], kProducerThreads / 32);   // one elected arrive per producer warp
             mbar_init(&a_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], kEpilogueThreads);
+            mbar_init(&acc_empty[b], kEpilogueThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -139,43 +153,104 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================================================================ A producers
-        const int r = threadIdx.x;
+        const int r = threadIdx.x & 127;           // row of the tile
+        const int jh = (threadIdx.x >> 7) * 4;     // this thread's chunks: jh .. jh+3
         const int swz = r & 7;
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int s = 0;
+        uint32_t ph = 0;
+
+        struct RowCtx { const typename L::In* xn; int oy, ox; bool valid; };
+        auto decode = [&](int64_t tile) {
+            RowCtx c;
             const int64_t m = tile * kRows + r;
-            const bool valid = m < g.m_total;
-            const int64_t n = valid ? m / g.P : 0;
-            const int pos = valid ? static_cast<int>(m - n * g.P) : 0;
-            const int oy = pos / g.OW, ox = pos - oy * g.OW;
+            c.valid = m < g.m_total;
+            const int64_t n = c.valid ? m / g.P : 0;
+            const int pos = c.valid ? static_cast<int>(m - n * g.P) : 0;
+            c.oy = pos / g.OW;
+            c.ox = pos - c.oy * g.OW;
             const int64_t img = rows != nullptr ? rows[n] : n;
-            const typename L::In* xn = X + img * (static_cast<int64_t>(g.C) * g.H * g.W);
-            for (int kb = 0; kb < kKB; ++kb, ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(&a_empty[s], ph ^ 1);
-                uint8_t* st = a_ring + s * S::kStageBytes + r * 128;
+            c.xn = X + img * (static_cast<int64_t>(g.C) * g.H * g.W);
+            return c;
+        };
+        using Raw = typename L::Raw;
+        auto fetch = [&](const RowCtx& c, int kb, Raw (&v)[4]) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 v = valid ? L::gather(xn, g, oy, ox, kb, j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int off = (j ^ swz) << 4;
-                    if (L::kTerms == 3) {
-                        float4 hi, lo;
-                        split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-                        split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-                        *reinterpret_cast<float4*>(st + off) = hi;
-                        *reinterpret_cast<float4*>(st + kTileBytes + off) = lo;
-                    } else {
-                        *reinterpret_cast<float4*>(st + off) = v;   // integers 0..255: exact in TF32
-                    }
+            for (int q = 0; q < 4; ++q) v[q] = c.valid ? L::gather(c.xn, g, c.oy, c.ox, kb, jh + q) : L::zero();
+        };
+
+        auto put = [&](const Raw (&c4)[4]) {       // write this thread's 4 chunks of one k-block
+            mbar_wait(&a_empty[s], ph ^ 1);
+            uint8_t* st = a_ring + s * S::kStageBytes + r * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = L::expand(c4[q]);
+                const int off = ((jh + q) ^ swz) << 4;
+                if (L::kTerms == 3) {
+                    float4 hi, lo;
+                    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+                    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(st + off) = hi;
+                    *reinterpret_cast<float4*>(st + kTileBytes + off) = lo;
+                } else {
+                    *reinterpret_cast<float4*>(st + off) = v;   // integers 0..255: exact in TF32
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&a_full[s]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);   // one arrive per warp (256 smem atomics would serialise)
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        };
+
+        int64_t tile = blockIdx.x;
+        RowCtx ctx = decode(tile);
+        if (sizeof(Raw) == 4) {
+            // small raw chunks (uint8 layer): prefetch a WHOLE TILE ahead - 32 words per thread - so a
+            // full memory round trip overlaps the 8 k-blocks of the current tile
+            Raw curT[kKB][4], nxtT[kKB][4];
+            if (tile < num_tiles) {
+#pragma unroll
+                for (int kb = 0; kb < kKB; ++kb) fetch(ctx, kb, curT[kb]);
+            }
+            while (tile < num_tiles) {
+                const int64_t tile_next = tile + gridDim.x;
+                if (tile_next < num_tiles) {
+                    ctx = decode(tile_next);
+#pragma unroll
+                    for (int kb = 0; kb < kKB; ++kb) fetch(ctx, kb, nxtT[kb]);
+                }
+#pragma unroll
+                for (int kb = 0; kb < kKB; ++kb) put(curT[kb]);
+#pragma unroll
+                for (int kb = 0; kb < kKB; ++kb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) curT[kb][q] = nxtT[kb][q];
+                tile = tile_next;
+            }
+        } else {
+            // 16-byte raw chunks (fp32 layer): one k-block ahead (register budget)
+            Raw cur[4], nxt[4];
+            if (tile < num_tiles) fetch(ctx, 0, cur);
+            while (tile < num_tiles) {
+                const int64_t tile_next = tile + gridDim.x;
+                RowCtx ctx_next = ctx;
+                for (int kb = 0; kb < kKB; ++kb) {
+                    if (kb + 1 < kKB) {
+                        fetch(ctx, kb + 1, nxt);
+                    } else if (tile_next < num_tiles) {
+                        ctx_next = decode(tile_next);
+                        fetch(ctx_next, 0, nxt);
+                    }
+                    put(cur);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+                }
+                tile = tile_next;
+                ctx = ctx_next;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // ================================================================ MMA issuer
         uint32_t it = 0, tcount = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -207,8 +282,8 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
             }
         }
     } else {
-        // ================================================================ epilogue (warps 4..7)
-        const int q = warp - 4;
+        // ================================================================ epilogue (warps 8..11)
+        const int q = warp - kEpiWarp0;
         const int r = q * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         uint32_t tcount = 0;
@@ -225,7 +300,8 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
                 tmem_ld32(tmem_base + lane_base + col, r0);       // 2 x 16 columns: both halves in one load
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
             const int64_t m = tile * kRows + r;
             if (m < g.m_total) {
                 const int64_t n = m / g.P;
@@ -244,7 +320,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
     }
 }

@@ -84,12 +84,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_tma[s], 1);
-            mbar_init(&full_mma[s], kSplitThreads);
+            mbar_init(&full_mma[s], kSplitThreads / 32);   // one elected arrive per split warp
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], kDrainThreads);
+            mbar_init(&tmem_empty[b], kDrainThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -168,7 +168,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 a_hi[idx] = va; a_lo[idx] = la; b_hi[idx] = vb; b_lo[idx] = lb;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async (tensor) proxy
-            mbar_arrive(&full_mma[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_mma[s]);
         }
     } else if (warp >= 8) {
         // ---- drain: promote each chunk's TMEM partial into fp32 registers (round-to-nearest adds)
@@ -190,7 +191,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(r[j]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&tmem_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
         // ---- epilogue: (+bias, ReLU) -> global
         const int row = m0 + q * 32 + lane;

@@ -161,7 +161,31 @@ def bench_replay(reps):
         speedup_sample=cpu_s / med, speedup_update=cpu_su / med_u)
 
 
-BENCHES = {"returns": bench_returns, "gemm": bench_gemm, "replay": bench_replay}
+def bench_conv(reps):
+    import torch.nn.functional as F
+    from rlpyt_b200.models import conv1_op
+    from rlpyt_b200.models.conv2_op import conv2_relu
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for N in (8192, 256):
+        x = torch.relu(torch.randn(N, 16, 20, 20, device="cuda", generator=g))
+        w = torch.randn(32, 16, 4, 4, device="cuda", generator=g) / 16
+        b = torch.randn(32, device="cuda", generator=g)
+        obs = torch.randint(0, 256, (N, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+        w1 = torch.randn(16, 4, 8, 8, device="cuda", generator=g) / 16
+        b1 = torch.randn(16, device="cuda", generator=g)
+        t_tc2, _ = timeit(lambda: conv2_relu(x, w, b), reps, flush=False)
+        t_cu2, _ = timeit(lambda: F.relu(F.conv2d(x, w, b, stride=2, padding=1)), reps, flush=False)
+        conv1_op.FORWARD_IMPL = "tc"
+        t_tc1, _ = timeit(lambda: conv1_op.conv1_u8_relu(w1, b1, obs, None), reps, flush=False)
+        conv1_op.FORWARD_IMPL = "simt"
+        t_si1, _ = timeit(lambda: conv1_op.conv1_u8_relu(w1, b1, obs, None), reps, flush=False)
+        conv1_op.FORWARD_IMPL = "tc"
+        t_cu1, _ = timeit(lambda: F.relu(F.conv2d(obs.float().mul_(1 / 255.), w1, b1, stride=4)), reps, flush=False)
+        out(kernel="conv fwd", N=N, conv2_tc_us=t_tc2 * 1e6, conv2_cudnn_us=t_cu2 * 1e6, conv1_tc_us=t_tc1 * 1e6,
+            conv1_simt_us=t_si1 * 1e6, conv1_cudnn_incl_convert_us=t_cu1 * 1e6)
+
+
+BENCHES = {"returns": bench_returns, "gemm": bench_gemm, "replay": bench_replay, "conv": bench_conv}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -86,5 +86,24 @@ def replay():
     torch.cuda.profiler.stop()
 
 
+def conv():
+    from rlpyt_b200.models.conv2_op import conv2_relu
+    from rlpyt_b200.models import conv1_op
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.relu(torch.randn(8192, 16, 20, 20, device="cuda", generator=g))
+    w = torch.randn(32, 16, 4, 4, device="cuda", generator=g) / 16
+    b = torch.randn(32, device="cuda", generator=g)
+    obs = torch.randint(0, 256, (8192, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    w1 = torch.randn(16, 4, 8, 8, device="cuda", generator=g) / 16
+    b1 = torch.randn(16, device="cuda", generator=g)
+    conv2_relu(x, w, b); conv1_op.conv1_u8_relu(w1, b1, obs, None)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    conv2_relu(x, w, b)
+    conv1_op.conv1_u8_relu(w1, b1, obs, None)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 if __name__ == "__main__":
-    {"ppo": ppo, "gae": gae, "replay": replay}[sys.argv[1]]()
+    {"ppo": ppo, "gae": gae, "replay": replay, "conv": conv}[sys.argv[1]]()
