@@ -216,6 +216,12 @@ int rl_conv1_u8_forward_tc(const uint8_t* obs, const int64_t* rows, const float*
                            float* out, int64_t N, int C, int H, int W, int relu, void* stream);
 int rl_conv2_forward_tc(const float* x, const float* weight, const float* bias, float* out, int64_t N,
                         int C, int IH, int IW, int relu, void* stream);
+/* Input gradient of the same layer (ConvolutionBackward wrt input): grad_out_masked [N,32,OH,OW] is
+ * grad_out * (out > 0); grad_x [N,16,IH,IW].  Four parity-class GEMMs (K = 32 channels x 2x2 taps) on
+ * the same tcgen05 kernel.  scratch: rl_conv2_dgrad_tc_scratch_bytes() bytes, 16B aligned. */
+int64_t rl_conv2_dgrad_tc_scratch_bytes(void);
+int rl_conv2_dgrad_tc(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C,
+                      int IH, int IW, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,11 @@
-"""``Conv2d(16->32, k4, s2, p1) + ReLU`` with the forward on the tensor cores (tcgen05 implicit GEMM,
-csrc/conv_tc.cu).  The backward (input and weight gradients) stays on cuDNN's fp32 kernels this
-round - see DESIGN.md section 6."""
+"""``Conv2d(16->32, k4, s2, p1) + ReLU`` on the tensor cores (csrc/conv_tc.cu): forward and input
+gradient are tcgen05 implicit GEMMs (the input gradient as four parity-class GEMMs); the weight
+gradient stays on cuDNN's fp32 kernel this round - see DESIGN.md section 6."""
 import torch
 
 from rlpyt_b200 import _lib
+
+_SCRATCH = {}
 
 
 def supported(layer, act):
@@ -30,10 +32,24 @@ class Conv2ReluTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight, out = ctx.saved_tensors
-        g = grad_out * (out > 0)
-        gx, gw, gb = torch.ops.aten.convolution_backward(
-            g, x, weight, [32], [2, 2], [1, 1], [1, 1], False, [0, 0], 1,
-            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
+        g = (grad_out * (out > 0)).contiguous()
+        gx = gw = gb = None
+        N, C, IH, IW = x.shape
+        if ctx.needs_input_grad[0]:
+            dev = x.device
+            scratch = _SCRATCH.get(str(dev))
+            if scratch is None:
+                scratch = torch.empty(int(_lib.load().rl_conv2_dgrad_tc_scratch_bytes()) // 4, dtype=torch.float32,
+                                      device=dev)
+                _SCRATCH[str(dev)] = scratch
+            gx = torch.empty_like(x)
+            with torch.cuda.device(dev):
+                _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx),
+                          N, C, IH, IW, _lib.ptr(scratch), _lib.stream(), n_launch=2)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            _gx, gw, gb = torch.ops.aten.convolution_backward(
+                g, x, weight, [32], [2, 2], [1, 1], [1, 1], False, [0, 0], 1,
+                [False, ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
         return gx, gw, gb
 
 
