@@ -222,6 +222,19 @@ int rl_conv2_forward_tc(const float* x, const float* weight, const float* bias, 
 int64_t rl_conv2_dgrad_tc_scratch_bytes(void);
 int rl_conv2_dgrad_tc(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C,
                       int IH, int IW, void* scratch, void* stream);
+/* Weight and bias gradients of both layers (ConvolutionBackward wrt weight/bias, with the ReLU mask of
+ * models/conv2d.py:41 folded in): one tcgen05 GEMM over all output positions,
+ *     grad_weight[oc][tap] = scale * sum_m im2col(x)[m][tap] * g[m][oc],   g = grad_out * (out > 0),
+ * taps on the MMA M axis (2 x 128), positions on the K axis, per-CTA partial sums promoted to fp32
+ * registers every 4 k-blocks and reduced in CTA order (deterministic).  out may be NULL when grad_out
+ * is already masked; grad_bias may be NULL.  grad_weight [16,4,8,8] / [32,16,4,4], grad_bias [16] / [32].
+ * scratch: rl_conv_wgrad_tc_scratch_bytes() bytes, 16B aligned.  Requires N*OH*OW < 2^31. */
+int64_t rl_conv_wgrad_tc_scratch_bytes(void);
+int rl_conv1_u8_wgrad_tc(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                         float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
+                         void* stream);
+int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, float* grad_weight,
+                      float* grad_bias, int64_t N, int C, int IH, int IW, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -114,6 +114,26 @@ struct Layer2 {                            // fp32 input, k4 s2 p1, 16 -> 32
         return v;
     }
     static constexpr float kScale = 1.0f;
+    // split addressing for the weight-gradient producers: element = image + row_off(position) + tap.off,
+    // the tap part is a per-thread constant there
+    struct Tap { int off, ky; };
+    __device__ static Tap tap(const Geom& g, int kb, int j) {
+        const int c = kb * 2 + (j >> 2), ky = j & 3;
+        return Tap{(c * g.H + ky - PAD) * g.W - PAD, ky};
+    }
+    __device__ static int row_off(const Geom& g, int oy, int ox) { return oy * S * g.W + ox * S; }
+    __device__ static float4 load(const float* __restrict__ p, const Tap& t, const Geom& g, int oy, int ox) {
+        const int iy = oy * S + t.ky - PAD, ix0 = ox * S - PAD;
+        const float* q = p + t.off;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < g.H) {
+            if (ix0 >= 0) v.x = q[0];
+            v.y = q[1];
+            if (ix0 + 2 < g.W) v.z = q[2];
+            if (ix0 + 3 < g.W) v.w = q[3];
+        }
+        return v;
+    }
 };
 
 struct Layer1 {                            // uint8 input, k8 s4 p0, 4 -> 16; pixels stay integers
@@ -125,7 +145,7 @@ struct Layer1 {                            // uint8 input, k8 s4 p0, 4 -> 16; pi
     using Raw = uint32_t;                  // 4 packed pixels; converted only when written to smem so the
                                            // load stays in flight across the previous stage's stores
     __device__ static uint32_t zero() { return 0u; }
-    __device__ static float4 expand(uint32_t v) {
+    __device__ static float4 expand(uint32_t v) {   // I2F.U8; a PRMT+FADD variant measured 7% slower
         return make_float4(static_cast<float>(v & 0xffu), static_cast<float>((v >> 8) & 0xffu),
                            static_cast<float>((v >> 16) & 0xffu), static_cast<float>(v >> 24));
     }
@@ -137,6 +157,15 @@ struct Layer1 {                            // uint8 input, k8 s4 p0, 4 -> 16; pi
         return *reinterpret_cast<const uint32_t*>(xn + (c * g.H + oy * S + ky) * g.W + ox * S + kx0);
     }
     static constexpr float kScale = 1.0f / 255.0f;
+    struct Tap { int off; };
+    __device__ static Tap tap(const Geom& g, int kb, int j) {
+        const int k0 = kb * 32 + j * 4;
+        return Tap{((k0 >> 6) * g.H + ((k0 >> 3) & 7)) * g.W + (k0 & 7)};
+    }
+    __device__ static int row_off(const Geom& g, int oy, int ox) { return oy * S * g.W + ox * S; }
+    __device__ static uint32_t load(const uint8_t* __restrict__ p, const Tap& t, const Geom&, int, int) {
+        return *reinterpret_cast<const uint32_t*>(p + t.off);
+    }
 };
 
 // Input gradient of layer 2 by input-pixel parity (see the header comment): rows = (parity, n, a, b).
@@ -434,6 +463,373 @@ static int launch(const typename L::In* X, const int64_t* rows, const float* W, 
     return check_launch("conv_fwd_tc_kernel");
 }
 
+
+// ====================================================================================================
+// Weight gradient as a tcgen05 GEMM over all output positions:
+//     D[tap, oc] = sum_m A[m, tap] * G[m, oc]        (A = im2col(X), G = ReLU-masked output gradient)
+// i.e. M_gemm = 256 taps (two 128-row MMA tiles), N_gemm = oc, K_gemm = m.  Both operands must be
+// K_gemm-major in shared memory (32 consecutive positions per 128-byte row):
+//   * A^T tile [128 taps x 32 m] per half: a producer thread gathers a 4-position x 4-tap block (four of
+//     the forward pass' row chunks), transposes it in registers and writes four tap rows; lanes run
+//     over consecutive positions of one tap chunk so the gathers stay coalesced;
+//   * G^T tile [oc x 32 m]: 16-byte reads of the NCHW gradient (positions are contiguous per channel).
+// Each persistent CTA owns a contiguous range of k-blocks (positions), accumulates in TMEM with the
+// same drain-to-fp32-registers promotion as gemm_tf32x3.cu (every kPromote k-blocks, two TMEM
+// buffers), and writes its partial D; wgrad_reduce_kernel sums the partials in CTA order
+// (deterministic), applies the layer scale and transposes to the [oc][tap] weight layout.
+constexpr int kWgStagesL2 = 2, kWgStagesL1 = 4, kPromote = 4;
+constexpr int kRowTab = 2048;              // row-index entries staged in shared memory per CTA (kRowMode 1)
+
+template <class L>
+struct WgSmem {
+    static constexpr int kATerms = (L::kTerms == 3) ? 2 : 1;
+    static constexpr int kABytes = 2 * kATerms * kTileBytes;          // two tap halves x (hi [+ lo])
+    static constexpr int kBTile = L::kN * 128;                        // G^T: oc rows x 128 B
+    static constexpr int kStageBytes = kABytes + 2 * kBTile;          // + G hi, lo
+    static constexpr int kStages = (L::kTerms == 3) ? kWgStagesL2 : kWgStagesL1;
+    static constexpr int kTotal = kStages * kStageBytes + 1024 + 256 + kRowTab * 8;
+};
+
+// kRowMode: 0 = images in order (rows == nullptr), 1 = this CTA's slice of the row-index table staged in
+// shared memory, 2 = row indices read from global memory (CTA spans more than kRowTab images).
+// A compile-time mode, not a runtime branch: a dependent global load in the fetch loop - even a
+// predicated-off one - makes its consumer wait on a scoreboard shared with the gathers still in flight
+// from the previous k-blocks, which serialises the whole prefetch (profiles/r01_wgrad_tc_notes.md).
+template <class L, int kRowMode>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restrict__ rows,
+                     const float* __restrict__ Out, const float* __restrict__ Gm, float* __restrict__ partial,
+                     float* __restrict__ partial_bias, Geom g) {
+    using S = WgSmem<L>;
+    using Rows = typename L::Rows;
+    constexpr int kStages = S::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+    uint64_t* s_full = bars;
+    uint64_t* s_empty = bars + kStages;
+    uint64_t* acc_full = bars + 2 * kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int64_t* row_tab = reinterpret_cast<int64_t*>(smem + kStages * S::kStageBytes + 256);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kIdesc = make_idesc_tf32(kRows, L::kN);
+    constexpr int kDepth = (sizeof(typename L::Raw) == 4) ? 3 : 2;   // k-blocks held in registers per producer
+
+    const int64_t total_kb = (g.m_total + 31) / 32;
+    const int64_t per_cta = (total_kb + gridDim.x - 1) / gridDim.x;
+    const int64_t kb_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
+    const int64_t kb_end = kb_begin + per_cta < total_kb ? kb_begin + per_cta : total_kb;
+    const int64_t my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+    const int64_t num_chunks = (my_kb + kPromote - 1) / kPromote;
+    const int64_t n_lo = (kb_begin * 32) / g.P;            // first image this CTA touches
+    if (kRowMode == 1) {
+        for (int i = threadIdx.x; i < kRowTab; i += kThreads) {
+            const int64_t n = n_lo + i;
+            row_tab[i] = n < g.n_img ? rows[n] : 0;
+        }
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], kProducerThreads / 32);
+            mbar_init(&s_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], kEpilogueThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ================================================================ producers
+        // thread -> (4-position chunk mc, 4-tap group tg of each half).  Lanes (2mc, 2mc+1) hold the
+        // two tap groups that share a 32-byte sector, 16 lanes cover the 32 positions of the k-block
+        // (coalesced gathers); the 8 lanes of one tap group write one full 128-byte row per store
+        // (conflict-free).  The same thread also owns kGP positions of one G^T row, chosen so that
+        // they are a subset of its own four positions (one decode serves both operands) and the G work
+        // is spread over all 256 threads (kN=16: two positions each, kN=32: four).
+        using Raw = typename L::Raw;
+        constexpr int kGP = L::kN / 8;                         // G positions per thread
+        const int mc = (lane >> 1) & 7;
+        const int tg = (lane & 1) + 2 * (lane >> 4) + 4 * warp;
+        const int g_oc = (tg * kGP) >> 2, g_r0 = (tg * kGP) & 3;
+        int s = 0;
+        uint32_t ph = 0;
+        float bias_acc = 0.0f;                         // sum of this thread's masked gradients (channel g_oc)
+
+        // running (image, output row, output column) of this thread's first position in the next
+        // k-block to fetch; advanced by 32 positions per fetch (fetches are issued in k-block order)
+        // with carries only - the loop has no division and the tap part of every address is a
+        // per-thread constant
+        const typename L::Tap tap0 = L::tap(g, tg >> 3, tg & 7), tap1 = L::tap(g, 4 + (tg >> 3), tg & 7);
+        const int adv_y = 32 / g.OW, adv_x = 32 - adv_y * g.OW;
+        int n_next, oy_next, ox_next;
+        {
+            const int64_t m0 = kb_begin * 32 + 4 * mc;
+            n_next = static_cast<int>(m0 / g.P);
+            const int pos = static_cast<int>(m0 - static_cast<int64_t>(n_next) * g.P);
+            oy_next = pos / g.OW;
+            ox_next = pos - oy_next * g.OW;
+        }
+        const int64_t img_stride = static_cast<int64_t>(g.C) * g.H * g.W;
+        const int n_lo32 = static_cast<int>(n_lo);
+        auto image_ptr = [&](int n) -> const typename L::In* {
+            int64_t img = n;
+            if (kRowMode == 1) img = row_tab[min(max(n - n_lo32, 0), kRowTab - 1)];
+            if (kRowMode == 2) img = n < g.n_img ? rows[n] : 0;
+            return X + img * img_stride;
+        };
+        const float* __restrict__ OutOrG = Out != nullptr ? Out : Gm;    // unconditional second load; the
+        const bool has_mask = Out != nullptr;                             // mask is applied when stored
+
+        struct Held { Raw a[2][4]; float gv[kGP]; float ov[kGP]; };
+        auto fetch = [&](Held& hd) {
+            int n = n_next, oy = oy_next, ox = ox_next;
+            const typename L::In* img_ptr = image_ptr(n);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool valid = n < g.n_img;
+                const typename L::In* p = img_ptr + L::row_off(g, oy, ox);
+                hd.a[0][r] = L::zero();
+                hd.a[1][r] = L::zero();
+                if (valid) {
+                    hd.a[0][r] = L::load(p, tap0, g, oy, ox);
+                    hd.a[1][r] = L::load(p, tap1, g, oy, ox);
+                }
+                if (++ox == g.OW) {
+                    ox = 0;
+                    if (++oy == g.OH) { oy = 0; ++n; img_ptr = image_ptr(n); }
+                }
+            }
+            // this thread's kGP positions of the G^T row start g_r0 positions into the chunk; they are
+            // walked separately so that the destination registers are static (a select on a runtime
+            // row index would consume the load at once and stall on its scoreboard)
+            {
+                int gn = n_next, goy = oy_next, gox = ox_next + g_r0;
+                while (gox >= g.OW) {
+                    gox -= g.OW;
+                    if (++goy == g.OH) { goy = 0; ++gn; }
+                }
+#pragma unroll
+                for (int j = 0; j < kGP; ++j) {
+                    float v = 0.0f, o = 1.0f;
+                    if (gn < g.n_img) {
+                        const int64_t gi = static_cast<int64_t>(gn * L::kN + g_oc) * g.P + (goy * g.OW + gox);
+                        v = Gm[gi];
+                        o = OutOrG[gi];
+                    }
+                    hd.gv[j] = v;
+                    hd.ov[j] = o;
+                    if (++gox == g.OW) {
+                        gox = 0;
+                        if (++goy == g.OH) { goy = 0; ++gn; }
+                    }
+                }
+            }
+            ox_next += adv_x;
+            oy_next += adv_y;
+            if (ox_next >= g.OW) { ox_next -= g.OW; ++oy_next; }
+            while (oy_next >= g.OH) { oy_next -= g.OH; ++n_next; }
+        };
+        auto put = [&](const Held& hd) {
+            mbar_wait(&s_empty[s], ph ^ 1);
+            uint8_t* st = smem + s * S::kStageBytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 f[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) f[r] = L::expand(hd.a[h][r]);
+                // transpose the 4 positions x 4 taps block: tap i <- (f[0][i], f[1][i], f[2][i], f[3][i])
+                const float4 t[4] = {make_float4(f[0].x, f[1].x, f[2].x, f[3].x), make_float4(f[0].y, f[1].y, f[2].y, f[3].y),
+                                     make_float4(f[0].z, f[1].z, f[2].z, f[3].z), make_float4(f[0].w, f[1].w, f[2].w, f[3].w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 4 * tg + i;
+                    uint8_t* dst = st + h * S::kATerms * kTileBytes + row * 128 + ((mc ^ (row & 7)) << 4);
+                    if (L::kTerms == 3) {
+                        float4 hi, lo;
+                        split_tf32(t[i].x, hi.x, lo.x); split_tf32(t[i].y, hi.y, lo.y);
+                        split_tf32(t[i].z, hi.z, lo.z); split_tf32(t[i].w, hi.w, lo.w);
+                        *reinterpret_cast<float4*>(dst) = hi;
+                        *reinterpret_cast<float4*>(dst + kTileBytes) = lo;
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = t[i];
+                    }
+                }
+            }
+            {
+                float hi[kGP], lo[kGP];
+#pragma unroll
+                for (int r = 0; r < kGP; ++r) {
+                    const float v = (!has_mask || hd.ov[r] > 0.0f) ? hd.gv[r] : 0.0f;
+                    bias_acc += v;
+                    split_tf32(v, hi[r], lo[r]);
+                }
+                uint8_t* dst = st + S::kABytes + g_oc * 128 + ((mc ^ (g_oc & 7)) << 4) + g_r0 * 4;
+                if (kGP == 4) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[kGP - 2], hi[kGP - 1]);
+                    *reinterpret_cast<float4*>(dst + S::kBTile) = make_float4(lo[0], lo[1], lo[kGP - 2], lo[kGP - 1]);
+                } else {
+                    *reinterpret_cast<float2*>(dst) = make_float2(hi[0], hi[1]);
+                    *reinterpret_cast<float2*>(dst + S::kBTile) = make_float2(lo[0], lo[1]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        };
+        Held held[kDepth];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d)
+            if (kb_begin + d < kb_end) fetch(held[d]);
+        for (int64_t kb = kb_begin; kb < kb_end; kb += kDepth) {
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                if (kb + d < kb_end) {
+                    put(held[d]);
+                    if (kb + d + kDepth < kb_end) fetch(held[d]);
+                }
+            }
+        }
+        // bias gradient: the threads of one channel are the lanes that differ in mc (and, for two
+        // positions per thread, in the low tap-group bit)
+        if (kGP == 2) bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 1);
+        bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 2);
+        bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 4);
+        bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 8);
+        if ((lane & 0xe) == 0 && (kGP == 4 || (lane & 1) == 0)) partial_bias[blockIdx.x * L::kN + g_oc] = bias_acc;
+    } else if (warp == kMmaWarp) {
+        // ================================================================ MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t c = 0; c < num_chunks; ++c) {
+            const int buf = static_cast<int>(c & 1);
+            mbar_wait(&acc_empty[buf], ((c >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t k0 = c * kPromote, k1 = (k0 + kPromote < my_kb) ? k0 + kPromote : my_kb;
+            for (int64_t kk = k0; kk < k1; ++kk) {
+                mbar_wait(&s_full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint8_t* st = smem + s * S::kStageBytes;
+                    const uint64_t db_hi = make_desc(st + S::kABytes), db_lo = make_desc(st + S::kABytes + S::kBTile);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 2 * L::kN + h * L::kN);
+                        const uint64_t da_hi = make_desc(st + h * S::kATerms * kTileBytes);
+                        const uint64_t da_lo = make_desc(st + h * S::kATerms * kTileBytes + kTileBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = static_cast<uint64_t>(k * 2);
+                            umma_tf32(acc, da_hi + adv, db_hi + adv, kIdesc, (kk > k0 || k > 0) ? 1u : 0u);
+                            umma_tf32(acc, da_hi + adv, db_lo + adv, kIdesc, 1u);
+                            if (L::kTerms == 3) umma_tf32(acc, da_lo + adv, db_hi + adv, kIdesc, 1u);
+                        }
+                    }
+                    umma_commit(&s_empty[s]);
+                    if (kk == k1 - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ================================================================ drain (warps 8..11): TMEM -> fp32 registers
+        const int q = warp - kEpiWarp0;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        float acc[2 * L::kN];
+#pragma unroll
+        for (int j = 0; j < 2 * L::kN; ++j) acc[j] = 0.0f;
+        for (int64_t c = 0; c < num_chunks; ++c) {
+            const int buf = static_cast<int>(c & 1);
+            mbar_wait(&acc_full[buf], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r0[32];
+            tmem_ld32(tmem_base + lane_base + static_cast<uint32_t>(buf * 2 * L::kN), r0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < 2 * L::kN) acc[j] += __uint_as_float(r0[j]);
+            if (L::kN == 32) {
+                uint32_t r1[32];
+                tmem_ld32(tmem_base + lane_base + static_cast<uint32_t>(buf * 2 * L::kN + 32), r1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r1[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        // partial[cta][tap][oc], tap = h*128 + 32*q + lane
+        float* out = partial + static_cast<int64_t>(blockIdx.x) * (256 * L::kN);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int oc = 0; oc < L::kN; ++oc) out[(h * 128 + q * 32 + lane) * L::kN + oc] = acc[h * L::kN + oc];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+// dW[oc][tap] = scale * sum_cta partial[cta][tap][oc];  db[oc] = sum_cta partial_bias[cta][oc]
+// (CTA order => deterministic; reads coalesced over oc, the 8 K-element transposed store is negligible)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias,
+                                    int nparts, int N, float scale, float* __restrict__ dW, float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over tap*N + oc
+    if (i < 256 * N) {
+        float s = 0.0f;
+        for (int b = 0; b < nparts; ++b) s += partial[static_cast<int64_t>(b) * 256 * N + i];
+        const int tap = i / N, oc = i - tap * N;
+        dW[oc * 256 + tap] = s * scale;
+    }
+    if (db != nullptr && i < N) {
+        float s = 0.0f;
+        for (int b = 0; b < nparts; ++b) s += partial_bias[b * N + i];
+        db[i] = s;
+    }
+}
+
+template <class L>
+static int launch_wgrad(const typename L::In* X, const int64_t* rows, const float* Out, const float* Gm, float* dW,
+                        float* db, float* scratch, Geom g, cudaStream_t st) {
+    using S = WgSmem<L>;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int64_t total_kb = (g.m_total + 31) / 32;
+    const int64_t grid = total_kb < sms ? total_kb : sms;
+    float* partial_bias = scratch + static_cast<int64_t>(sms) * 256 * 32;
+    const int64_t per_cta = (total_kb + grid - 1) / grid;
+    const int mode = rows == nullptr ? 0 : ((per_cta * 32 + 35) / g.P + 2 <= kRowTab ? 1 : 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_wgrad_tc_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        cudaFuncSetAttribute(conv_wgrad_tc_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        cudaFuncSetAttribute(conv_wgrad_tc_kernel<L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        attr_set = true;
+    }
+    auto kern = mode == 0 ? conv_wgrad_tc_kernel<L, 0> : mode == 1 ? conv_wgrad_tc_kernel<L, 1> : conv_wgrad_tc_kernel<L, 2>;
+    kern<<<static_cast<unsigned>(grid), kThreads, S::kTotal, st>>>(X, rows, Out, Gm, scratch, partial_bias, g);
+    int rc = check_launch("conv_wgrad_tc_kernel");
+    if (rc != RL_OK) return rc;
+    wgrad_reduce_kernel<<<(256 * L::kN + 255) / 256, 256, 0, st>>>(scratch, partial_bias, static_cast<int>(grid), L::kN,
+                                                                   L::kScale, dW, db);
+    return check_launch("wgrad_reduce_kernel");
+}
+
 // B_p[par][c][oc*4 + ty*2 + tx] = W[oc][c][ky(py,ty)][kx(px,tx)], tap(parity 0) = {1,3}, tap(parity 1) = {0,2}
 __global__ void conv2_dgrad_prep_kernel(const float* __restrict__ W, float* __restrict__ Bp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over 4*16*128
@@ -475,6 +871,39 @@ int rl_conv2_forward_tc(const float* x, const float* weight, const float* bias, 
     g.n_img = static_cast<int>(N); g.C = C; g.H = IH; g.W = IW;
     g.OH = (IH + 2 - 4) / 2 + 1; g.OW = (IW + 2 - 4) / 2 + 1; g.P = g.OH * g.OW; g.m_total = N * g.P; g.BH = g.BW = 0;
     return rl::convtc::launch<rl::convtc::Layer2>(x, nullptr, weight, bias, out, g, relu, rl::as_stream(stream));
+}
+
+int64_t rl_conv_wgrad_tc_scratch_bytes(void) {
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    return static_cast<int64_t>(sms) * (256 * 32 + 32) * static_cast<int64_t>(sizeof(float));
+}
+
+int rl_conv1_u8_wgrad_tc(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                         float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
+                         void* stream) {
+    RL_REQUIRE(obs && grad_out && grad_weight && scratch, RL_EINVAL, "rl_conv1_u8_wgrad_tc: null pointer");
+    RL_REQUIRE(N >= 1 && C == 4 && H >= 8 && W >= 8 && W % 4 == 0, RL_EINVAL,
+               "rl_conv1_u8_wgrad_tc: needs C=4, W %% 4 == 0 (got C=%d H=%d W=%d)", C, H, W);
+    rl::convtc::Geom g;
+    g.n_img = static_cast<int>(N); g.C = C; g.H = H; g.W = W;
+    g.OH = (H - 8) / 4 + 1; g.OW = (W - 8) / 4 + 1; g.P = g.OH * g.OW; g.m_total = N * g.P; g.BH = g.BW = 0;
+    RL_REQUIRE(g.m_total < (int64_t(1) << 31) - 64, RL_EINVAL, "rl_conv1_u8_wgrad_tc: N*OH*OW must be < 2^31");
+    return rl::convtc::launch_wgrad<rl::convtc::Layer1>(obs, rows, out, grad_out, grad_weight, grad_bias,
+                                                        static_cast<float*>(scratch), g, rl::as_stream(stream));
+}
+
+int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, float* grad_weight,
+                      float* grad_bias, int64_t N, int C, int IH, int IW, void* scratch, void* stream) {
+    RL_REQUIRE(x && grad_out && grad_weight && scratch, RL_EINVAL, "rl_conv2_wgrad_tc: null pointer");
+    RL_REQUIRE(N >= 1 && C == 16 && IH >= 2 && IW >= 2, RL_EINVAL, "rl_conv2_wgrad_tc: needs C=16 (got C=%d %dx%d)", C,
+               IH, IW);
+    rl::convtc::Geom g;
+    g.n_img = static_cast<int>(N); g.C = C; g.H = IH; g.W = IW;
+    g.OH = (IH + 2 - 4) / 2 + 1; g.OW = (IW + 2 - 4) / 2 + 1; g.P = g.OH * g.OW; g.m_total = N * g.P; g.BH = g.BW = 0;
+    RL_REQUIRE(g.m_total < (int64_t(1) << 31) - 64, RL_EINVAL, "rl_conv2_wgrad_tc: N*OH*OW must be < 2^31");
+    return rl::convtc::launch_wgrad<rl::convtc::Layer2>(x, nullptr, out, grad_out, grad_weight, grad_bias,
+                                                        static_cast<float*>(scratch), g, rl::as_stream(stream));
 }
 
 int64_t rl_conv2_dgrad_tc_scratch_bytes(void) { return 4 * 16 * 128 * static_cast<int64_t>(sizeof(float)); }

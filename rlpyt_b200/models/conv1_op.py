@@ -10,6 +10,8 @@ from rlpyt_b200 import _lib
 _SCRATCH = {}
 # forward implementation: "tc" = tcgen05 implicit GEMM (csrc/conv_tc.cu), "simt" = fp32 kernel (csrc/conv1.cu)
 FORWARD_IMPL = os.environ.get("RLPYT_B200_CONV1_FWD", "tc")
+# weight gradient: "tc" = tcgen05 GEMM over positions (csrc/conv_tc.cu), "simt" = fp32 kernel (csrc/conv1.cu)
+WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
 
 
 def supported(image_shape, conv_layers):
@@ -49,6 +51,16 @@ class Conv1U8Relu(torch.autograd.Function):
         R, C, H, W = obs.shape
         N = out.shape[0]
         dev = obs.device
+        if WGRAD_IMPL == "tc":
+            from rlpyt_b200.models.conv2_op import wgrad_scratch
+            gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
+            gb = torch.empty(16, dtype=torch.float32, device=dev)
+            g = grad_out.contiguous()
+            with torch.cuda.device(dev):
+                _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g),
+                          _lib.ptr(gw), _lib.ptr(gb), N, C, H, W, _lib.ptr(wgrad_scratch(dev)), _lib.stream(),
+                          n_launch=2)
+            return gw, gb, None, None
         key = str(dev)
         scratch = _SCRATCH.get(key)
         if scratch is None:

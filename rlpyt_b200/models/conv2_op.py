@@ -1,11 +1,24 @@
 """``Conv2d(16->32, k4, s2, p1) + ReLU`` on the tensor cores (csrc/conv_tc.cu): forward and input
-gradient are tcgen05 implicit GEMMs (the input gradient as four parity-class GEMMs); the weight
-gradient stays on cuDNN's fp32 kernel this round - see DESIGN.md section 6."""
+gradient are tcgen05 implicit GEMMs (the input gradient as four parity-class GEMMs), and so is the
+weight gradient (taps x channels GEMM over all positions; ``RLPYT_B200_CONV_WGRAD=cudnn`` selects
+cuDNN's fp32 kernel for comparison)."""
+import os
+
 import torch
 
 from rlpyt_b200 import _lib
 
 _SCRATCH = {}
+WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
+
+
+def wgrad_scratch(dev):
+    key = ("wgrad", str(dev))
+    scratch = _SCRATCH.get(key)
+    if scratch is None:
+        scratch = torch.empty(int(_lib.load().rl_conv_wgrad_tc_scratch_bytes()) // 4, dtype=torch.float32, device=dev)
+        _SCRATCH[key] = scratch
+    return scratch
 
 
 def supported(layer, act):
@@ -46,7 +59,13 @@ class Conv2ReluTC(torch.autograd.Function):
             with torch.cuda.device(dev):
                 _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx),
                           N, C, IH, IW, _lib.ptr(scratch), _lib.stream(), n_launch=2)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc":
+            gw = torch.empty_like(weight)
+            gb = torch.empty(32, dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x), None, _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gb),
+                          N, C, IH, IW, _lib.ptr(wgrad_scratch(x.device)), _lib.stream(), n_launch=2)
+        elif ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             _gx, gw, gb = torch.ops.aten.convolution_backward(
                 g, x, weight, [32], [2, 2], [1, 1], [1, 1], False, [0, 0], 1,
                 [False, ctx.needs_input_grad[1], ctx.needs_input_grad[2]])

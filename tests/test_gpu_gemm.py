@@ -105,3 +105,62 @@ def test_conv1_forward_tcgen05_vs_simt(shape, use_rows):
     scale = float(F.conv2d(x.abs(), w.double().abs(), None, stride=4).max())
     assert float((y_tc.double() - ref).abs().max()) <= 3e-6 * scale
     np.testing.assert_allclose(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("shape,n_obs,n_rows", [((4, 84, 84), 70, None), ((4, 84, 84), 300, 130), ((4, 36, 36), 5, None),
+                                                ((4, 104, 80), 33, 40), ((4, 8, 8), 3, None)])
+def test_conv1_wgrad_tcgen05_vs_fp64(shape, n_obs, n_rows):
+    """Weight/bias gradient of the uint8 first layer as a tcgen05 GEMM over positions (pixels exact in
+    TF32, gradient split hi/lo, fp32 promotion every 4 k-blocks) against an fp64 reference with the
+    same ReLU mask; 1e-5 of the term-magnitude scale."""
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    from rlpyt_b200.models.conv2_op import wgrad_scratch
+    g = torch.Generator(device="cuda").manual_seed(n_obs)
+    obs = torch.randint(0, 256, (n_obs,) + shape, dtype=torch.uint8, device="cuda", generator=g)
+    rows = torch.randint(0, n_obs, (n_rows,), device="cuda", generator=g) if n_rows else None
+    N = n_rows or n_obs
+    OH, OW = (shape[1] - 8) // 4 + 1, (shape[2] - 8) // 4 + 1
+    out = torch.randn(N, 16, OH, OW, device="cuda", generator=g)          # sign = ReLU mask
+    go = torch.randn(N, 16, OH, OW, device="cuda", generator=g)
+    gw = torch.full((16, 4, 8, 8), float("nan"), device="cuda")
+    gb = torch.full((16,), float("nan"), device="cuda")
+    _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(go), _lib.ptr(gw),
+              _lib.ptr(gb), N, 4, shape[1], shape[2], _lib.ptr(wgrad_scratch(obs.device)), _lib.stream(), n_launch=2)
+    x = ((obs if rows is None else obs[rows]).double() / 255).requires_grad_(False)
+    gm = (go * (out > 0)).double()
+    w = torch.zeros(16, 4, 8, 8, dtype=torch.float64, device="cuda", requires_grad=True)
+    b = torch.zeros(16, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(x, w, b, stride=4).backward(gm)
+    wa = torch.zeros_like(w, requires_grad=True)
+    F.conv2d(x, wa, None, stride=4).backward(gm.abs())
+    scale_w = float(wa.grad.max())
+    assert float((gw.double() - w.grad).abs().max()) <= 1e-5 * scale_w
+    assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())
+
+
+@pytest.mark.parametrize("N,plane", [(1, (20, 20)), (64, (20, 20)), (700, (20, 20)), (300, (25, 19)), (2, (7, 5))])
+def test_conv2_wgrad_tcgen05_vs_fp64(N, plane):
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    from rlpyt_b200.models.conv2_op import wgrad_scratch
+    g = torch.Generator(device="cuda").manual_seed(N)
+    x = torch.relu(torch.randn((N, 16) + plane, device="cuda", generator=g))
+    OH, OW = (plane[0] - 2) // 2 + 1, (plane[1] - 2) // 2 + 1
+    out = torch.randn(N, 32, OH, OW, device="cuda", generator=g)
+    go = torch.randn(N, 32, OH, OW, device="cuda", generator=g)
+    for masked_in_kernel in (True, False):
+        gw = torch.full((32, 16, 4, 4), float("nan"), device="cuda")
+        gb = torch.full((32,), float("nan"), device="cuda")
+        gin = go if masked_in_kernel else (go * (out > 0)).contiguous()
+        _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x), _lib.ptr(out) if masked_in_kernel else None, _lib.ptr(gin),
+                  _lib.ptr(gw), _lib.ptr(gb), N, 16, plane[0], plane[1], _lib.ptr(wgrad_scratch(x.device)),
+                  _lib.stream(), n_launch=2)
+        gm = (go * (out > 0)).double()
+        w = torch.zeros(32, 16, 4, 4, dtype=torch.float64, device="cuda", requires_grad=True)
+        b = torch.zeros(32, dtype=torch.float64, device="cuda", requires_grad=True)
+        F.conv2d(x.double(), w, b, stride=2, padding=1).backward(gm)
+        wa = torch.zeros_like(w, requires_grad=True)
+        F.conv2d(x.double(), wa, None, stride=2, padding=1).backward(gm.abs())
+        assert float((gw.double() - w.grad).abs().max()) <= 1e-5 * float(wa.grad.max())
+        assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())

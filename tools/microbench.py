@@ -183,9 +183,59 @@ def bench_conv(reps):
         t_cu1, _ = timeit(lambda: F.relu(F.conv2d(obs.float().mul_(1 / 255.), w1, b1, stride=4)), reps, flush=False)
         out(kernel="conv fwd", N=N, conv2_tc_us=t_tc2 * 1e6, conv2_cudnn_us=t_cu2 * 1e6, conv1_tc_us=t_tc1 * 1e6,
             conv1_simt_us=t_si1 * 1e6, conv1_cudnn_incl_convert_us=t_cu1 * 1e6)
+        # backward pieces: weight gradient on tcgen05 vs the SIMT (layer 1) / cuDNN (layer 2) kernels
+        from rlpyt_b200 import _lib
+        from rlpyt_b200.models.conv2_op import wgrad_scratch
+        o1 = torch.randn(N, 16, 20, 20, device="cuda", generator=g)
+        g1 = torch.randn(N, 16, 20, 20, device="cuda", generator=g)
+        o2 = torch.randn(N, 32, 10, 10, device="cuda", generator=g)
+        g2 = (torch.randn(N, 32, 10, 10, device="cuda", generator=g) * (o2 > 0)).contiguous()
+        gw1, gb1 = torch.empty_like(w1), torch.empty_like(b1)
+        gw2, gb2 = torch.empty_like(w), torch.empty_like(b)
+        sc = wgrad_scratch(x.device)
+        sc1 = torch.empty(int(_lib.load().rl_conv1_u8_wgrad_scratch_bytes()) // 4, device="cuda")
+        t_w1, _ = timeit(lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), None, _lib.ptr(o1), _lib.ptr(g1),
+                                           _lib.ptr(gw1), _lib.ptr(gb1), N, 4, 84, 84, _lib.ptr(sc), _lib.stream()),
+                         reps, flush=False)
+        t_w1s, _ = timeit(lambda: _lib.call("rl_conv1_u8_wgrad", _lib.ptr(obs), None, _lib.ptr(o1), _lib.ptr(g1),
+                                            _lib.ptr(gw1), _lib.ptr(gb1), N, 4, 84, 84, 1, _lib.ptr(sc1),
+                                            _lib.stream()), reps, flush=False)
+        t_w2, _ = timeit(lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x), None, _lib.ptr(g2), _lib.ptr(gw2),
+                                           _lib.ptr(gb2), N, 16, 20, 20, _lib.ptr(sc), _lib.stream()), reps,
+                         flush=False)
+        t_w2c, _ = timeit(lambda: torch.ops.aten.convolution_backward(
+            g2, x, w, [32], [2, 2], [1, 1], [1, 1], False, [0, 0], 1, [False, True, True]), reps, flush=False)
+        out(kernel="conv wgrad", N=N, conv1_tc_us=t_w1 * 1e6, conv1_simt_us=t_w1s * 1e6, conv2_tc_us=t_w2 * 1e6,
+            conv2_cudnn_us=t_w2c * 1e6)
 
 
-BENCHES = {"returns": bench_returns, "gemm": bench_gemm, "replay": bench_replay, "conv": bench_conv}
+def bench_wgrad(reps):
+    """tcgen05 weight-gradient kernels only (tuning runs: RLPYT_B200_WG_DEPTH=1..4)."""
+    from rlpyt_b200 import _lib
+    from rlpyt_b200.models.conv2_op import wgrad_scratch
+    g = torch.Generator(device="cuda").manual_seed(0)
+    N = 8192
+    x = torch.relu(torch.randn(N, 16, 20, 20, device="cuda", generator=g))
+    obs = torch.randint(0, 256, (N, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    o1 = torch.randn(N, 16, 20, 20, device="cuda", generator=g)
+    g1 = torch.randn(N, 16, 20, 20, device="cuda", generator=g)
+    g2 = torch.randn(N, 32, 10, 10, device="cuda", generator=g)
+    gw1, gb1 = torch.empty(16, 4, 8, 8, device="cuda"), torch.empty(16, device="cuda")
+    gw2, gb2 = torch.empty(32, 16, 4, 4, device="cuda"), torch.empty(32, device="cuda")
+    sc = wgrad_scratch(x.device)
+    t1, _ = timeit(lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), None, _lib.ptr(o1), _lib.ptr(g1),
+                                     _lib.ptr(gw1), _lib.ptr(gb1), N, 4, 84, 84, _lib.ptr(sc), _lib.stream()),
+                   reps, flush=False)
+    t2, _ = timeit(lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x), None, _lib.ptr(g2), _lib.ptr(gw2),
+                                     _lib.ptr(gb2), N, 16, 20, 20, _lib.ptr(sc), _lib.stream()), reps, flush=False)
+    rows = torch.randperm(N, device="cuda", generator=g)
+    t1r, _ = timeit(lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1),
+                                      _lib.ptr(gw1), _lib.ptr(gb1), N, 4, 84, 84, _lib.ptr(sc), _lib.stream()),
+                    reps, flush=False)
+    out(kernel="conv wgrad tc", conv1_us=t1 * 1e6, conv1_rows_us=t1r * 1e6, conv2_us=t2 * 1e6)
+
+
+BENCHES = {"wgrad": bench_wgrad, "returns": bench_returns, "gemm": bench_gemm, "replay": bench_replay, "conv": bench_conv}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -105,5 +105,26 @@ def conv():
     torch.cuda.profiler.stop()
 
 
+def convbwd():
+    """Backward of both conv layers: tcgen05 weight gradients (both) and the layer-2 input gradient."""
+    from rlpyt_b200.models.conv2_op import conv2_relu
+    from rlpyt_b200.models import conv1_op
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.randint(0, 256, (8192, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    w1 = (torch.randn(16, 4, 8, 8, device="cuda", generator=g) / 16).requires_grad_(True)
+    b1 = torch.randn(16, device="cuda", generator=g).requires_grad_(True)
+    w = (torch.randn(32, 16, 4, 4, device="cuda", generator=g) / 16).requires_grad_(True)
+    b = torch.randn(32, device="cuda", generator=g).requires_grad_(True)
+    go = torch.randn(8192, 32, 10, 10, device="cuda", generator=g)
+    for i in range(2):
+        if i == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        y = conv2_relu(conv1_op.conv1_u8_relu(w1, b1, obs, None), w, b)
+        y.backward(go)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 if __name__ == "__main__":
-    {"ppo": ppo, "gae": gae, "replay": replay, "conv": conv}[sys.argv[1]]()
+    {"ppo": ppo, "gae": gae, "replay": replay, "conv": conv, "convbwd": convbwd}[sys.argv[1]]()
