@@ -249,7 +249,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     using Rows = typename L::Rows;
     constexpr int kKB = L::kKB, kK = L::kKB * 32;
     const int64_t num_tiles = Rows::num_tiles(g);
@@ -288,7 +288,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp < 8) {
         // ================================================================ A producers
@@ -388,7 +388,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
                 const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(&a_full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                if (elect_one()) {
                     const int half = kb / (kKB / 2);
                     const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 2 * L::kN + half * L::kN);
                     const uint8_t* st = a_ring + s * S::kStageBytes;
@@ -512,7 +512,7 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     int64_t* row_tab = reinterpret_cast<int64_t*>(smem + kStages * S::kStageBytes + 256);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr uint32_t kIdesc = make_idesc_tf32(kRows, L::kN);
     constexpr int kDepth = (sizeof(typename L::Raw) == 4) ? 3 : 2;   // k-blocks held in registers per producer
 
@@ -549,7 +549,7 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp < 8) {
         // ================================================================ producers
@@ -722,7 +722,7 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
             for (int64_t kk = k0; kk < k1; ++kk) {
                 mbar_wait(&s_full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint8_t* st = smem + s * S::kStageBytes;
                     const uint64_t db_hi = make_desc(st + S::kABytes), db_lo = make_desc(st + S::kABytes + S::kBTile);
 #pragma unroll

@@ -72,7 +72,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint64_t* tmem_empty = tmem_full + 2;      // [2] accumulator drained (drain -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     // split-K (small M): blockIdx.z owns k-blocks [kb0, kb0 + num_kb) and writes its partial tile to
     // slice z of the workspace C[z][M][N]; splitk_reduce_kernel sums the slices in order.
@@ -102,7 +102,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -131,7 +131,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(&full_mma[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                if (elect_one()) {
                     uint8_t* st = smem + s * kStageBytes;
                     const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
                     const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);

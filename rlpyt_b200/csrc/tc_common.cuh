@@ -56,6 +56,25 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// One elected lane of a converged warp.  The MMA issue loops run warp-uniform and wrap the tcgen05
+// instructions in `if (elect_one())` rather than `if (lane == 0)`: with a lane test the compiler has to
+// treat descriptors / TMEM addresses as per-thread values and emits an ELECT + 5x R2UR.BROADCAST retry
+// loop around every UTCHMMA (~15 dependent instructions per MMA, the issue warp became the critical
+// path of the conv kernels); under elect.sync the operands stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+// warp index / a value read by every lane, as warp-uniform values the compiler can keep in uniform registers
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
