@@ -236,6 +236,14 @@ int rl_conv1_u8_wgrad_tc(const uint8_t* obs, const int64_t* rows, const float* o
 int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, float* grad_weight,
                       float* grad_bias, int64_t N, int C, int IH, int IW, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ layer helpers (HBM-bound)
+ * rl_relu_backward_f32: dst[i] = out[i] > 0 ? grad[i] : 0 - the backward of the torch.nn.ReLU that
+ *   follows every conv / linear layer (rlpyt/models/conv2d.py:41, rlpyt/models/mlp.py:33) in one pass.
+ * rl_transpose_f32: dst[cols,rows] = src[rows,cols]^T - operand re-layout for the weight-gradient GEMM
+ *   (rl_gemm_tf32x3_f32 wants the reduction axis contiguous in both operands). */
+int rl_relu_backward_f32(const float* grad, const float* out, float* dst, int64_t n, void* stream);
+int rl_transpose_f32(const float* src, float* dst, int64_t rows, int64_t cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

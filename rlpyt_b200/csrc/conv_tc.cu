@@ -295,6 +295,7 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
         const int r = threadIdx.x & 127;           // row of the tile
         const int jh = (threadIdx.x >> 7) * 4;     // this thread's chunks: jh .. jh+3
         const int swz = r & 7;
+        const uint32_t a_ring_u32 = smem_u32(a_ring);
         int s = 0;
         uint32_t ph = 0;
 
@@ -307,19 +308,19 @@ conv_fwd_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __restri
 
         auto put = [&](const Raw (&c4)[4]) {       // write this thread's 4 chunks of one k-block
             mbar_wait(&a_empty[s], ph ^ 1);
-            uint8_t* st = a_ring + s * S::kStageBytes + r * 128;
+            const uint32_t st = a_ring_u32 + static_cast<uint32_t>(s * S::kStageBytes + r * 128);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 v = L::expand(c4[q]);
-                const int off = ((jh + q) ^ swz) << 4;
+                const uint32_t off = static_cast<uint32_t>(((jh + q) ^ swz) << 4);
                 if (L::kTerms == 3) {
                     float4 hi, lo;
                     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
                     split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(st + off) = hi;
-                    *reinterpret_cast<float4*>(st + kTileBytes + off) = lo;
+                    sts128(st + off, hi);
+                    sts128(st + kTileBytes + off, lo);
                 } else {
-                    *reinterpret_cast<float4*>(st + off) = v;   // integers 0..255: exact in TF32
+                    sts128(st + off, v);                        // integers 0..255: exact in TF32
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -564,6 +565,7 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
         const int mc = (lane >> 1) & 7;
         const int tg = (lane & 1) + 2 * (lane >> 4) + 4 * warp;
         const int g_oc = (tg * kGP) >> 2, g_r0 = (tg * kGP) & 3;
+        const uint32_t smem_base_u32 = smem_u32(smem);
         int s = 0;
         uint32_t ph = 0;
         float bias_acc = 0.0f;                         // sum of this thread's masked gradients (channel g_oc)
@@ -584,9 +586,10 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
         }
         const int64_t img_stride = static_cast<int64_t>(g.C) * g.H * g.W;
         const int n_lo32 = static_cast<int>(n_lo);
+        const uint32_t row_tab_u32 = smem_u32(row_tab);
         auto image_ptr = [&](int n) -> const typename L::In* {
             int64_t img = n;
-            if (kRowMode == 1) img = row_tab[min(max(n - n_lo32, 0), kRowTab - 1)];
+            if (kRowMode == 1) img = lds_s64(row_tab_u32 + static_cast<uint32_t>(min(max(n - n_lo32, 0), kRowTab - 1)) * 8u);
             if (kRowMode == 2) img = n < g.n_img ? rows[n] : 0;
             return X + img * img_stride;
         };
@@ -644,7 +647,7 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
         };
         auto put = [&](const Held& hd) {
             mbar_wait(&s_empty[s], ph ^ 1);
-            uint8_t* st = smem + s * S::kStageBytes;
+            const uint32_t st = smem_base_u32 + static_cast<uint32_t>(s * S::kStageBytes);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float4 f[4];
@@ -656,15 +659,15 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = 4 * tg + i;
-                    uint8_t* dst = st + h * S::kATerms * kTileBytes + row * 128 + ((mc ^ (row & 7)) << 4);
+                    const uint32_t dst = st + static_cast<uint32_t>(h * S::kATerms * kTileBytes + row * 128 + ((mc ^ (row & 7)) << 4));
                     if (L::kTerms == 3) {
                         float4 hi, lo;
                         split_tf32(t[i].x, hi.x, lo.x); split_tf32(t[i].y, hi.y, lo.y);
                         split_tf32(t[i].z, hi.z, lo.z); split_tf32(t[i].w, hi.w, lo.w);
-                        *reinterpret_cast<float4*>(dst) = hi;
-                        *reinterpret_cast<float4*>(dst + kTileBytes) = lo;
+                        sts128(dst, hi);
+                        sts128(dst + kTileBytes, lo);
                     } else {
-                        *reinterpret_cast<float4*>(dst) = t[i];
+                        sts128(dst, t[i]);
                     }
                 }
             }
@@ -676,13 +679,13 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
                     bias_acc += v;
                     split_tf32(v, hi[r], lo[r]);
                 }
-                uint8_t* dst = st + S::kABytes + g_oc * 128 + ((mc ^ (g_oc & 7)) << 4) + g_r0 * 4;
+                const uint32_t dst = st + static_cast<uint32_t>(S::kABytes + g_oc * 128 + ((mc ^ (g_oc & 7)) << 4) + g_r0 * 4);
                 if (kGP == 4) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[kGP - 2], hi[kGP - 1]);
-                    *reinterpret_cast<float4*>(dst + S::kBTile) = make_float4(lo[0], lo[1], lo[kGP - 2], lo[kGP - 1]);
+                    sts128(dst, make_float4(hi[0], hi[1], hi[kGP - 2], hi[kGP - 1]));
+                    sts128(dst + S::kBTile, make_float4(lo[0], lo[1], lo[kGP - 2], lo[kGP - 1]));
                 } else {
-                    *reinterpret_cast<float2*>(dst) = make_float2(hi[0], hi[1]);
-                    *reinterpret_cast<float2*>(dst + S::kBTile) = make_float2(lo[0], lo[1]);
+                    sts64(dst, make_float2(hi[0], hi[1]));
+                    sts64(dst + S::kBTile, make_float2(lo[0], lo[1]));
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -785,21 +788,32 @@ conv_wgrad_tc_kernel(const typename L::In* __restrict__ X, const int64_t* __rest
     }
 }
 
-// dW[oc][tap] = scale * sum_cta partial[cta][tap][oc];  db[oc] = sum_cta partial_bias[cta][oc]
-// (CTA order => deterministic; reads coalesced over oc, the 8 K-element transposed store is negligible)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias,
-                                    int nparts, int N, float scale, float* __restrict__ dW, float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over tap*N + oc
-    if (i < 256 * N) {
-        float s = 0.0f;
-        for (int b = 0; b < nparts; ++b) s += partial[static_cast<int64_t>(b) * 256 * N + i];
-        const int tap = i / N, oc = i - tap * N;
-        dW[oc * 256 + tap] = s * scale;
+// dW[oc][tap] = scale * sum_cta partial[cta][tap][oc];  db[oc] = sum_cta partial_bias[cta][oc].
+// 64 outputs x 4 partial groups per block: each thread sums every 4th partial in CTA order, the four
+// group sums are combined in a fixed order (deterministic); reads coalesced over oc.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias, int nparts, int N,
+                    float scale, float* __restrict__ dW, float* __restrict__ db) {
+    __shared__ float sh[4][64];
+    const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + o;                        // over tap*N + oc, then N bias entries
+    const int total = 256 * N;
+    float s = 0.0f;
+    if (i < total) {
+        for (int b = grp; b < nparts; b += 4) s += partial[static_cast<int64_t>(b) * total + i];
+    } else if (i < total + N && db != nullptr) {
+        for (int b = grp; b < nparts; b += 4) s += partial_bias[b * N + (i - total)];
     }
-    if (db != nullptr && i < N) {
-        float s = 0.0f;
-        for (int b = 0; b < nparts; ++b) s += partial_bias[b * N + i];
-        db[i] = s;
+    sh[grp][o] = s;
+    __syncthreads();
+    if (grp == 0) {
+        const float r = (sh[0][o] + sh[1][o]) + (sh[2][o] + sh[3][o]);
+        if (i < total) {
+            const int tap = i / N, oc = i - tap * N;
+            dW[oc * 256 + tap] = r * scale;
+        } else if (i < total + N && db != nullptr) {
+            db[i - total] = r;
+        }
     }
 }
 
@@ -825,7 +839,7 @@ static int launch_wgrad(const typename L::In* X, const int64_t* rows, const floa
     kern<<<static_cast<unsigned>(grid), kThreads, S::kTotal, st>>>(X, rows, Out, Gm, scratch, partial_bias, g);
     int rc = check_launch("conv_wgrad_tc_kernel");
     if (rc != RL_OK) return rc;
-    wgrad_reduce_kernel<<<(256 * L::kN + 255) / 256, 256, 0, st>>>(scratch, partial_bias, static_cast<int>(grid), L::kN,
+    wgrad_reduce_kernel<<<(256 * L::kN + L::kN + 63) / 64, 256, 0, st>>>(scratch, partial_bias, static_cast<int>(grid), L::kN,
                                                                    L::kScale, dW, db);
     return check_launch("wgrad_reduce_kernel");
 }

@@ -154,18 +154,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int s = kb % kStages;
             const uint32_t ph = (kb / kStages) & 1;
             mbar_wait(&full_tma[s], ph);
-            uint8_t* st = smem + s * kStageBytes;
-            float4* a_hi = reinterpret_cast<float4*>(st);
-            float4* a_lo = reinterpret_cast<float4*>(st + kTileBytes);
-            float4* b_hi = reinterpret_cast<float4*>(st + 2 * kTileBytes);
-            float4* b_lo = reinterpret_cast<float4*>(st + 3 * kTileBytes);
+            const uint32_t st = smem_u32(smem + s * kStageBytes) + static_cast<uint32_t>(t) * 16u;
 #pragma unroll
             for (int i = 0; i < kTileBytes / 16 / kSplitThreads; ++i) {   // 8 float4 per thread per tile
-                const int idx = t + i * kSplitThreads;
-                float4 va = a_hi[idx], la, vb = b_hi[idx], lb;
+                const uint32_t a = st + static_cast<uint32_t>(i * kSplitThreads) * 16u;
+                float4 va = lds128(a), la, vb = lds128(a + 2 * kTileBytes), lb;
                 split4(va, la);
                 split4(vb, lb);
-                a_hi[idx] = va; a_lo[idx] = la; b_hi[idx] = vb; b_lo[idx] = lb;
+                sts128(a, va); sts128(a + kTileBytes, la); sts128(a + 2 * kTileBytes, vb); sts128(a + 3 * kTileBytes, lb);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async (tensor) proxy
             __syncwarp();

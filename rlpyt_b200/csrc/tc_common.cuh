@@ -56,6 +56,30 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Explicit shared-space accesses with 32-bit addresses.  The operand tiles live in 1024-byte-aligned
+// dynamic shared memory reached through integer pointer arithmetic, for which the compiler loses the
+// address space and emits generic LD.E / ST.E (long-scoreboard loads, "lg throttle" on the stores);
+// these keep the hot loops on LDS / STS.
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)
+                 : "memory");
+    return v;
+}
+
+__device__ __forceinline__ int64_t lds_s64(uint32_t addr) {
+    int64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // One elected lane of a converged warp.  The MMA issue loops run warp-uniform and wrap the tcgen05
 // instructions in `if (elect_one())` rather than `if (lane == 0)`: with a lane test the compiler has to
 // treat descriptors / TMEM addresses as per-thread values and emits an ELECT + 5x R2UR.BROADCAST retry

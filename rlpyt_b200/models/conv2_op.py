@@ -7,6 +7,7 @@ import os
 import torch
 
 from rlpyt_b200 import _lib
+from rlpyt_b200.models.gemm_op import relu_backward
 
 _SCRATCH = {}
 WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
@@ -45,7 +46,7 @@ class Conv2ReluTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight, out = ctx.saved_tensors
-        g = (grad_out * (out > 0)).contiguous()
+        g = relu_backward(grad_out, out)
         gx = gw = gb = None
         N, C, IH, IW = x.shape
         if ctx.needs_input_grad[0]:

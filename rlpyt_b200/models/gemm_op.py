@@ -1,7 +1,8 @@
 """``torch.nn.Linear`` (+ReLU) over the fp32-accurate tensor-core GEMM of csrc/gemm_tf32x3.cu
 (tcgen05 kind::tf32, 3-term hi/lo split, TMA-staged, TMEM accumulators): forward, input gradient
 and weight gradient all run on the same "TN" kernel (C = A B^T, K contiguous in both operands);
-the backward operands are re-laid-out with plain transposes (HBM-bound, small next to the GEMM)."""
+the backward operands are re-laid-out with the tiled transpose of csrc/layers.cu (HBM-bound, small
+next to the GEMM) and the ReLU backward is one fused pass."""
 import torch
 
 from rlpyt_b200 import _lib
@@ -31,6 +32,27 @@ def gemm_tn(a, b, bias=None, relu=False):
     return out
 
 
+def relu_backward(grad, out):
+    """grad * (out > 0) in one pass (csrc/layers.cu)."""
+    _lib.require_cuda(grad, out)
+    grad, out = grad.contiguous(), out.contiguous()
+    dst = torch.empty_like(grad)
+    with torch.cuda.device(grad.device):
+        _lib.call("rl_relu_backward_f32", _lib.ptr(grad), _lib.ptr(out), _lib.ptr(dst), grad.numel(), _lib.stream())
+    return dst
+
+
+def transpose2d(x):
+    """Contiguous transpose of a 2-D fp32 CUDA tensor."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    rows, cols = x.shape
+    dst = torch.empty((cols, rows), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("rl_transpose_f32", _lib.ptr(x), _lib.ptr(dst), rows, cols, _lib.stream())
+    return dst
+
+
 def usable(in_features, out_features):
     return in_features % 4 == 0 and out_features % 4 == 0
 
@@ -50,14 +72,14 @@ class LinearTf32x3(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         gy = gy.contiguous()
         if ctx.relu:
-            gy = gy * (y > 0)
+            gy = relu_backward(gy, y)
         gx = gw = gb = None
         M = x.shape[0]
         if ctx.needs_input_grad[0]:
-            gx = gemm_tn(gy, weight.detach().t().contiguous())            # [M,N] x [K,N]^T
+            gx = gemm_tn(gy, transpose2d(weight.detach()))            # [M,N] x [K,N]^T
         if ctx.needs_input_grad[1]:
             if M % 4 == 0:
-                gw = gemm_tn(gy.t().contiguous(), x.detach().t().contiguous())   # [N,M] x [K,M]^T
+                gw = gemm_tn(transpose2d(gy), transpose2d(x.detach()))   # [N,M] x [K,M]^T
             else:
                 gw = gy.t().mm(x.detach())
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -164,3 +164,25 @@ def test_conv2_wgrad_tcgen05_vs_fp64(N, plane):
         F.conv2d(x.double(), wa, None, stride=2, padding=1).backward(gm.abs())
         assert float((gw.double() - w.grad).abs().max()) <= 1e-5 * float(wa.grad.max())
         assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())
+
+
+@pytest.mark.parametrize("shape", [(0,), (1,), (7,), (8192, 512), (33, 5, 7)])
+def test_relu_backward_bit_exact(shape):
+    from rlpyt_b200.models.gemm_op import relu_backward
+    g = torch.Generator(device="cuda").manual_seed(3)
+    grad = torch.randn(shape, device="cuda", generator=g)
+    out = torch.relu(torch.randn(shape, device="cuda", generator=g))
+    got = relu_backward(grad, out)
+    assert torch.equal(got, grad * (out > 0))
+    if grad.numel() > 8:      # 4-byte-aligned views take the scalar path
+        flat_g, flat_o = grad.reshape(-1)[1:], out.reshape(-1)[1:]
+        assert torch.equal(relu_backward(flat_g, flat_o), flat_g * (flat_o > 0))
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (5, 3), (32, 32), (33, 65), (8192, 512), (512, 3200), (1000, 17)])
+def test_transpose_bit_exact(rows, cols):
+    from rlpyt_b200.models.gemm_op import transpose2d
+    x = torch.randn(rows, cols, device="cuda", generator=torch.Generator(device="cuda").manual_seed(rows))
+    got = transpose2d(x)
+    assert got.shape == (cols, rows) and got.is_contiguous()
+    assert torch.equal(got, x.t().contiguous())
