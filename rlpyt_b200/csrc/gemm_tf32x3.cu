@@ -58,6 +58,10 @@ __device__ __forceinline__ void split4(float4& v, float4& lo) {
     v = hi;
 }
 
+// kRawHi: leave the TMA-loaded fp32 tile in place as the "hi" operand (the tensor core ignores the low
+// 13 mantissa bits of a TF32 operand, i.e. it sees trunc(x) - exactly the hi term split_tf32 would
+// write) and only write the lo tile: one third less split-warp shared-memory traffic.
+template <bool kRawHi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    float* __restrict__ C, const float* __restrict__ bias, int M, int N, int K, int relu,
@@ -161,7 +165,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 float4 va = lds128(a), la, vb = lds128(a + 2 * kTileBytes), lb;
                 split4(va, la);
                 split4(vb, lb);
-                sts128(a, va); sts128(a + kTileBytes, la); sts128(a + 2 * kTileBytes, vb); sts128(a + 3 * kTileBytes, lb);
+                if (!kRawHi) { sts128(a, va); sts128(a + 2 * kTileBytes, vb); }
+                sts128(a + kTileBytes, la); sts128(a + 3 * kTileBytes, lb);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async (tensor) proxy
             __syncwarp();
@@ -298,10 +303,18 @@ int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float*
     if (rc != RL_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(rl::gemm::gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(rl::gemm::gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             rl::gemm::kSmemBytes);
+        cudaFuncSetAttribute(rl::gemm::gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              rl::gemm::kSmemBytes);
         attr_set = true;
     }
+    static int raw_hi = -1;
+    if (raw_hi < 0) {
+        const char* e = getenv("RLPYT_B200_GEMM_RAW_HI");
+        raw_hi = e ? atoi(e) : 1;
+    }
+    auto kern = raw_hi ? rl::gemm::gemm_tf32x3_kernel<true> : rl::gemm::gemm_tf32x3_kernel<false>;
     const int64_t ws_bytes = rl_gemm_tf32x3_workspace_bytes(M, N, K);
     const int total_kb = static_cast<int>((K + rl::gemm::BK - 1) / rl::gemm::BK);
     int splits = static_cast<int>(ws_bytes / (M * N * static_cast<int64_t>(sizeof(float))));
@@ -312,13 +325,13 @@ int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float*
     dim3 grid(static_cast<unsigned>((N + rl::gemm::BN - 1) / rl::gemm::BN),
               static_cast<unsigned>((M + rl::gemm::BM - 1) / rl::gemm::BM), static_cast<unsigned>(splits));
     if (splits == 1) {
-        rl::gemm::gemm_tf32x3_kernel<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
+        kern<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
             ma, mb, C, bias, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), relu, total_kb);
         return rl::check_launch("gemm_tf32x3_kernel");
     }
     RL_REQUIRE(rl::aligned(workspace, 16), RL_EALIGN, "rl_gemm_tf32x3_f32: workspace must be 16B aligned");
     float* ws = static_cast<float*>(workspace);
-    rl::gemm::gemm_tf32x3_kernel<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
+    kern<<<grid, rl::gemm::kThreads, rl::gemm::kSmemBytes, st>>>(
         ma, mb, ws, nullptr, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), 0, kb_per_split);
     rc = rl::check_launch("gemm_tf32x3_kernel");
     if (rc != RL_OK) return rc;
