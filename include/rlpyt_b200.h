@@ -236,6 +236,20 @@ int rl_conv1_u8_wgrad_tc(const uint8_t* obs, const int64_t* rows, const float* o
 int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, float* grad_weight,
                       float* grad_bias, int64_t N, int C, int IH, int IW, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ DQN loss
+ * rlpyt/algos/dqn/dqn.py:230-263 `DQN.loss` after the two network forwards: Q(s,a) selection, (double-)DQN
+ * target, y = return_ + (1 - done_n) * disc_n * target_q, Huber loss with threshold delta_clip (delta_clip < 0:
+ * plain 0.5*delta^2), optional importance weights, loss = mean, td_abs_errors = clamp(|delta|, 0, delta_clip)
+ * (bit-identical per-sample fp32 arithmetic - these are the new priorities), and grad_qs = dloss/dqs [N,A].
+ * qs/target_qs/next_qs [N,A] f32 (next_qs NULL: no double-DQN), action [N] i64, return_ [N] f32, done_n [N] u8,
+ * is_weights [N] f32 or NULL, disc_n = (float)(discount ** n_step_return); out_scalars[2] = {loss, N};
+ * grad_qs may be NULL.  scratch: rl_dqn_loss_scratch_bytes(N) bytes, 8B aligned.  A <= 64. */
+int64_t rl_dqn_loss_scratch_bytes(int64_t N);
+int rl_dqn_loss_f32(const float* qs, const float* target_qs, const float* next_qs, const int64_t* action,
+                    const float* return_, const uint8_t* done_n, const float* is_weights, int64_t N, int A,
+                    float disc_n, float delta_clip, float* out_scalars, float* td_abs_errors, float* grad_qs,
+                    void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ layer helpers (HBM-bound)
  * rl_relu_backward_f32: dst[i] = out[i] > 0 ? grad[i] : 0 - the backward of the torch.nn.ReLU that
  *   follows every conv / linear layer (rlpyt/models/conv2d.py:41, rlpyt/models/mlp.py:33) in one pass.

@@ -50,6 +50,8 @@ SIGNATURES = {
     "rl_conv2_forward_tc": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "rl_conv2_dgrad_tc_scratch_bytes": (c_int64, []),
     "rl_conv2_dgrad_tc": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P, P]),
+    "rl_dqn_loss_scratch_bytes": (c_int64, [c_int64]),
+    "rl_dqn_loss_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float, P, P, P, P, P]),
     "rl_relu_backward_f32": (c_int, [P, P, P, c_int64, P]),
     "rl_transpose_f32": (c_int, [P, P, c_int64, c_int64, P]),
     "rl_conv_wgrad_tc_scratch_bytes": (c_int64, []),

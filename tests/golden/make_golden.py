@@ -445,7 +445,85 @@ def gen_replay():
     _save("replay", out)
 
 
-GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay}
+# --------------------------------------------------------------------------- DQN loss
+DQN_CASES = [
+    # name, seed, N, A, double_dqn, prioritized, delta_clip, n_step, discount
+    ("dqn_small", 40, 7, 4, False, False, 1.0, 1, 0.99),
+    ("dqn_double_pri", 41, 512, 6, True, True, 1.0, 3, 0.99),
+    ("dqn_pri", 42, 512, 6, False, True, 1.0, 3, 0.99),
+    ("dqn_mse", 43, 33, 18, True, False, None, 1, 0.997),
+    ("dqn_clip_frac", 44, 257, 9, True, True, 0.1, 5, 0.95),
+    ("dqn_n1", 45, 1, 2, False, True, 1.0, 1, 0.99),
+]
+
+
+def dqn_inputs(seed, N, A):
+    """Q-values with ties (argmax/first-index semantics), |delta| on both sides of the clip and exactly on it."""
+    rng = np.random.default_rng(seed)
+    qs = (rng.standard_normal((N, A)) * 1.5).astype(np.float32)
+    target_qs = (rng.standard_normal((N, A)) * 1.5).astype(np.float32)
+    next_qs = (rng.standard_normal((N, A)) * 1.5).astype(np.float32)
+    if N > 4:
+        next_qs[1, :] = next_qs[1, 0]                    # all equal: argmax -> 0
+        next_qs[2, -1] = next_qs[2].max()                # duplicate maximum at the end
+        target_qs[3, :] = target_qs[3, 0]
+    action = rng.integers(0, A, size=N).astype(np.int64)
+    return_ = rng.standard_normal(N).astype(np.float32)
+    done_n = rng.random(N) < 0.1
+    is_weights = rng.random(N).astype(np.float32) * 0.9 + 0.1
+    if N > 6:                                            # |delta| == delta_clip exactly and delta == 0
+        done_n[5], done_n[6] = True, True
+        return_[5] = qs[5, action[5]] + np.float32(1.0)
+        return_[6] = qs[6, action[6]]
+    return qs, target_qs, next_qs, action, return_, done_n, is_weights
+
+
+def gen_dqn():
+    import torch
+    from rlpyt.algos.dqn.dqn import DQN
+    from rlpyt.agents.base import AgentInputs
+    from collections import namedtuple
+
+    class StubAgent:
+        """Fixed network outputs: the reference's DQN.loss arithmetic and autograd run unmodified.
+        The online net is called first on agent_inputs (tag 0), then on target_inputs (tag 1)."""
+
+        def __init__(self, qs, next_qs, target_qs):
+            self.qs, self.next_qs, self.target_qs = qs, next_qs, target_qs
+
+        def __call__(self, observation, prev_action, prev_reward):
+            return self.qs if int(observation[0]) == 0 else self.next_qs
+
+        def target(self, observation, prev_action, prev_reward):
+            return self.target_qs
+
+    Samples = namedtuple("Samples", "agent_inputs action return_ done done_n target_inputs is_weights")
+    out = {}
+    for name, seed, N, A, double, pri, clip, n_step, discount in DQN_CASES:
+        qs, target_qs, next_qs, action, return_, done_n, is_weights = dqn_inputs(seed, N, A)
+        for k, x in dict(qs=qs, target_qs=target_qs, next_qs=next_qs, action=action, return_=return_,
+                         done_n=done_n, is_weights=is_weights).items():
+            out[f"{name}/{k}"] = x
+        out[f"{name}/hyper"] = np.array([float(double), float(pri), -1.0 if clip is None else clip, n_step, discount],
+                                        np.float64)
+        q = torch.from_numpy(qs).clone().requires_grad_(True)
+        algo = DQN(discount=discount, delta_clip=clip, n_step_return=n_step, double_dqn=double,
+                   prioritized_replay=pri)
+        algo.mid_batch_reset = True
+        algo.agent = StubAgent(q, torch.from_numpy(next_qs), torch.from_numpy(target_qs))
+        tag0 = AgentInputs(torch.zeros(N), torch.zeros(N), torch.zeros(N))
+        tag1 = AgentInputs(torch.ones(N), torch.zeros(N), torch.zeros(N))
+        samples = Samples(tag0, torch.from_numpy(action), torch.from_numpy(return_), torch.from_numpy(done_n),
+                          torch.from_numpy(done_n), tag1, torch.from_numpy(is_weights))
+        loss, td_abs = algo.loss(samples)
+        loss.backward()
+        out[f"{name}/loss"] = np.array([loss.item()], np.float64)
+        out[f"{name}/td_abs_errors"] = td_abs.numpy().copy()
+        out[f"{name}/grad_qs"] = q.grad.numpy().copy()
+    _save("dqn", out)
+
+
+GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay, "dqn": gen_dqn}
 
 
 def main():
