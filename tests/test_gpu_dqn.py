@@ -21,7 +21,7 @@ def _c(x):
 
 def _check(c, loss, td, grad):
     assert np.array_equal(td.cpu().numpy(), c["td_abs_errors"])             # priorities: bit-exact
-    np.testing.assert_allclose(float(loss), c["loss"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(float(loss.detach()), c["loss"], rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(grad.cpu().numpy(), c["grad_qs"], rtol=RTOL, atol=1e-9)
 
 
