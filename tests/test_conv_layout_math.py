@@ -1,0 +1,142 @@
+"""Index mathematics of the tcgen05 convolution kernels (csrc/conv_tc.cu), restated in numpy and checked
+on the CPU: the GEMM formulations (implicit-GEMM forward, parity-class input gradient, taps x positions
+weight gradient) against torch's convolution derivatives in fp64, and the producer thread -> shared-memory
+mappings (SWIZZLE_128B chunk placement) as exact covers of the operand tiles.  These are the host-side
+invariants the CUDA code relies on; the kernels themselves are tested on the GPU (test_gpu_gemm.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def im2col(x, k, s, p):
+    """[N,C,H,W] -> A[m = (n,oy,ox), tap = (c,ky,kx)] - the GEMM row/column order of the kernels."""
+    N, C, H, W = x.shape
+    cols = F.unfold(x, kernel_size=k, stride=s, padding=p)          # [N, C*k*k, P], taps ordered (c,ky,kx)
+    return cols.permute(0, 2, 1).reshape(-1, C * k * k)
+
+
+@pytest.mark.parametrize("geom", [dict(C=4, OC=16, k=8, s=4, p=0, H=36, W=44), dict(C=16, OC=32, k=4, s=2, p=1, H=20, W=20),
+                                  dict(C=16, OC=32, k=4, s=2, p=1, H=7, W=5)])
+def test_forward_and_wgrad_gemm_formulations(geom):
+    g = torch.Generator().manual_seed(0)
+    C, OC, k, s, p, H, W = (geom[n] for n in "C OC k s p H W".split())
+    x = torch.randn(3, C, H, W, dtype=torch.float64, generator=g)
+    w = torch.randn(OC, C, k, k, dtype=torch.float64, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, stride=s, padding=p)
+    A = im2col(x, k, s, p)                                            # [M, K]
+    Y = A @ w.detach().reshape(OC, -1).T                              # forward: rows = positions
+    np.testing.assert_allclose(Y.reshape(3, -1, OC).permute(0, 2, 1).reshape(y.shape).numpy(), y.detach().numpy(),
+                               rtol=1e-12, atol=1e-12)
+    go = torch.randn(y.shape, dtype=torch.float64, generator=g)
+    y.backward(go)
+    G = go.permute(0, 2, 3, 1).reshape(-1, OC)                        # g[m, oc]
+    D = A.T @ G                                                       # wgrad: D[tap, oc], reduction over positions
+    np.testing.assert_allclose(D.T.reshape(w.shape).numpy(), w.grad.numpy(), rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("H,W", [(20, 20), (25, 19), (7, 5), (2, 2)])
+def test_dgrad_parity_decomposition(H, W):
+    """Input gradient of Conv2d(16->32,k4,s2,p1) as four GEMMs, one per input-pixel parity (py,px): pixel
+    (2a+py, 2b+px) receives taps ky in {1,3} (py=0) or {0,2} (py=1) from output rows a+dpos - the
+    Dgrad2 policy's ``dpos`` table - and likewise in x; K = 32 channels x 2 x 2 taps."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 16, H, W, dtype=torch.float64, generator=g, requires_grad=True)
+    w = torch.randn(32, 16, 4, 4, dtype=torch.float64, generator=g)
+    y = F.conv2d(x, w, stride=2, padding=1)
+    go = torch.randn(y.shape, dtype=torch.float64, generator=g)
+    y.backward(go)
+    OH, OW = y.shape[2:]
+    dpos = lambda parity, t: (0 if t == 0 else -1) if parity == 0 else (1 if t == 0 else 0)
+    ktap = lambda parity, t: (1 if t == 0 else 3) if parity == 0 else (0 if t == 0 else 2)
+    dx = torch.zeros_like(x)
+    gon, wn = go.numpy(), w.numpy()
+    out = dx.numpy()
+    for py in range(2):
+        for px in range(2):
+            for iy in range(py, H, 2):
+                for ix in range(px, W, 2):
+                    a, b = iy // 2, ix // 2
+                    acc = np.zeros((2, 16))
+                    for ty in range(2):
+                        for tx in range(2):
+                            oy, ox = a + dpos(py, ty), b + dpos(px, tx)
+                            if 0 <= oy < OH and 0 <= ox < OW:
+                                acc += gon[:, :, oy, ox] @ wn[:, :, ktap(py, ty), ktap(px, tx)]
+                    out[:, :, iy, ix] = acc
+    np.testing.assert_allclose(out, x.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def swizzled(row, chunk):
+    """Byte offset of 16-byte chunk ``chunk`` of row ``row`` in a K-major SWIZZLE_128B tile (128 B rows)."""
+    return row * 128 + ((chunk ^ (row & 7)) << 4)
+
+
+def test_forward_producer_mapping_covers_tile():
+    """conv_fwd_tc_kernel: thread -> (row r = tid & 127, chunks jh..jh+3 with jh = (tid >> 7) * 4)."""
+    seen = set()
+    for tid in range(256):
+        r, jh = tid & 127, (tid >> 7) * 4
+        for q in range(4):
+            seen.add(swizzled(r, jh + q))
+    assert seen == {16 * i for i in range(128 * 8)}
+
+
+@pytest.mark.parametrize("kN", [16, 32])
+def test_wgrad_producer_mapping_covers_tiles(kN):
+    """conv_wgrad_tc_kernel: thread -> (4-position chunk mc, tap group tg); A^T rows are taps, G^T rows are
+    output channels; every 16-byte (A^T) / kGP*4-byte (G^T) slot is written exactly once, and the eight
+    lanes of one tap group fill one whole 128-byte row (conflict-free stores)."""
+    kGP = kN // 8
+    a_slots, g_slots = [], []
+    for warp in range(8):
+        for lane in range(32):
+            mc = (lane >> 1) & 7
+            tg = (lane & 1) + 2 * (lane >> 4) + 4 * warp
+            for i in range(4):
+                a_slots.append(swizzled(4 * tg + i, mc))
+            g_oc, g_r0 = (tg * kGP) >> 2, (tg * kGP) & 3
+            base = swizzled(g_oc, mc) + 4 * g_r0
+            g_slots += [base + 4 * j for j in range(kGP)]
+            assert 0 <= g_oc < kN and g_r0 + kGP <= 4
+    assert sorted(a_slots) == [16 * i for i in range(128 * 8)]                 # one tap half: 128 rows x 8 chunks
+    assert sorted(g_slots) == [4 * i for i in range(kN * 32)]                  # kN rows x 32 positions
+    # lanes of a quarter-warp store phase (8 lanes) hit 8 distinct 16-byte bank groups
+    for warp in range(8):
+        for phase in range(4):
+            lanes = range(8 * phase, 8 * phase + 8)
+            offs = {swizzled(4 * ((l & 1) + 2 * (l >> 4) + 4 * warp), (l >> 1) & 7) % 128 for l in lanes}
+            assert len(offs) == 8
+
+
+def test_wgrad_position_walk_matches_division():
+    """The carry-only (image, oy, ox) walk of the wgrad producers equals m -> (m // P, (m % P) // OW, m % OW)
+    for every k-block, chunk and row, including P < 32 and P = 1."""
+    for OH, OW in [(20, 20), (25, 19), (10, 10), (2, 3), (1, 1)]:
+        P = OH * OW
+        adv_y, adv_x = 32 // OW, 32 - (32 // OW) * OW
+        for mc in range(8):
+            for kb_begin in (0, 5):
+                m0 = kb_begin * 32 + 4 * mc
+                n, pos = divmod(m0, P)
+                oy, ox = divmod(pos, OW)
+                for kb in range(kb_begin, kb_begin + 40):
+                    nn, yy, xx = n, oy, ox
+                    for r in range(4):
+                        m = kb * 32 + 4 * mc + r
+                        assert (nn, yy, xx) == (m // P, (m % P) // OW, m % OW)
+                        xx += 1
+                        if xx == OW:
+                            xx = 0
+                            yy += 1
+                            if yy == OH:
+                                yy = 0
+                                nn += 1
+                    ox += adv_x
+                    oy += adv_y
+                    if ox >= OW:
+                        ox -= OW
+                        oy += 1
+                    while oy >= OH:
+                        oy -= OH
+                        n += 1
