@@ -1,5 +1,7 @@
-// Convolution forward as an IMPLICIT GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32 with the
-// fp32-accurate hi/lo split of gemm_tf32x3.cu) for the two conv layers of the AtariFf network.
+// Convolutions as IMPLICIT GEMMs on the 5th-gen tensor cores (tcgen05, kind::tf32 with the
+// fp32-accurate hi/lo split of gemm_tf32x3.cu) for the two conv layers of the AtariFf network:
+// forward of both layers, input gradient of layer 2, weight + bias gradients of both layers
+// (the weight-gradient kernel has its own header comment further down).
 //
 // Reference: rlpyt/models/conv2d.py:36-44 with the defaults of rlpyt/models/pg/atari_ff_model.py:31-35:
 //   layer 1: uint8 frames [N,4,H,W] -> *1/255 -> Conv2d(4->16, k8, s4, p0) + ReLU
@@ -18,7 +20,8 @@
 //     the integers 0..255 - exact in TF32, so A needs no lo term - and applies 1/255 in the epilogue.
 //   * B (the filter bank, [oc][256] = the weight tensor as stored) is split and swizzled into shared
 //     memory once per persistent CTA.
-//   * MMA warp: per k-block 4 x (2|3) tcgen05.mma (M=128, N=16|32, K=8); the two halves of K go to
+//   * MMA warp: per k-block 4 x (2|3) tcgen05.mma (M=128, N=16|32, K=8), issued from warp-uniform code
+//     under elect.sync so descriptors stay in uniform registers (tc_common.cuh); the two halves of K go to
 //     separate TMEM accumulators that the epilogue adds in fp32 (halves the accumulator truncation),
 //     and the accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * epilogue (4 warps): tcgen05.ld -> (+bias, *scale, ReLU) -> NCHW stores, coalesced over positions.
@@ -27,8 +30,10 @@
 // 2x2 subset of the 4x4 taps - into four dense GEMMs with K = 32 channels x 4 taps = 128 whose rows are
 // the input pixels of that parity, A gathers the ReLU-masked output gradient, B_p[c][oc*4+t] is the
 // matching slice of the filter bank (rl_conv2_dgrad_tc prepares the four B_p).
-// Measured per 8192-sample minibatch: layer-2 forward 0.33 ms (cuDNN fp32 0.68 ms), layer-1 forward
-// 0.61 ms (fp32 SIMT kernel of conv1.cu 0.82 ms; cuDNN incl. the u8->f32 conversion 3.2 ms).
+// Measured per 8192-sample minibatch (round 1): layer-1 forward 0.45 ms (fp32 SIMT
+// kernel of conv1.cu 0.82 ms; cuDNN incl. the u8->f32 conversion 3.2 ms), layer-2 forward 0.29 ms (cuDNN
+// fp32 0.68 ms), layer-2 input gradient 0.60 ms (cuDNN 1.06 ms), weight gradients 0.78 / 0.30 ms
+// (SIMT 1.06 ms / cuDNN 0.79 ms).
 #include "tc_common.cuh"
 
 namespace rl {

@@ -1,6 +1,8 @@
-"""``Conv2d(4->16, k8, s4) + ReLU`` on uint8 frames as one autograd op over the hand-written kernels
-of csrc/conv1.cu (forward fused with the row gather and the ``/255`` scaling; backward = weight and
-bias gradients - the input is an observation and needs none)."""
+"""``Conv2d(4->16, k8, s4) + ReLU`` on uint8 frames as one autograd op over the hand-written kernels:
+forward (fused with the minibatch row gather and the ``/255`` scaling) and backward (weight and bias
+gradients with the ReLU mask folded in - the input is an observation and needs no gradient) run on the
+tcgen05 kernels of csrc/conv_tc.cu by default; the fp32 SIMT kernels of csrc/conv1.cu remain
+selectable for cross-checks (``RLPYT_B200_CONV1_FWD=simt``, ``RLPYT_B200_CONV_WGRAD=simt``)."""
 import os
 
 import torch
