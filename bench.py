@@ -216,7 +216,12 @@ def run_b200(args):
     if rank == 0:
         out["roofline"] = roofline_gae(U)
         try:   # the largest kernel of the timed step, for context next to the metric's own kernel above
-            out["roofline_step_kernel"] = roofline_conv1_wgrad()
+            rk = roofline_conv1_wgrad()
+            n_updates = int(PPO_KW.get("epochs", 4)) * int(PPO_KW.get("minibatches", 4))
+            # share of the timed step spent in this kernel (one launch per minibatch update), to compare
+            # with the ncu launch list under profiles/ (serialised, cold-cache: the share must agree)
+            rk["share_of_step"] = rk["us_per_launch"] * n_updates / (out["ms_per_step"] * 1e3)
+            out["roofline_step_kernel"] = rk
         except Exception as e:  # never let the extra measurement break the bench line
             out["roofline_step_kernel"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
