@@ -26,7 +26,7 @@ from rlpyt_b200.samplers.collectors import GpuResetCollector
 from rlpyt_b200.samplers.rollout import DeviceRollout
 from rlpyt_b200.utils.collections import AttrDict
 from rlpyt_b200.utils.seed import set_seed, set_envs_seeds
-from rlpyt_b200.utils.synchronize import drain_queue
+from rlpyt_b200.utils.synchronize import drain_queue, SpinSemaphore
 
 _mp = mp.get_context("fork")
 
@@ -106,8 +106,16 @@ class GpuSampler(BaseSampler):
             itr=_mp.RawValue(ctypes.c_long, 0),
         )
         self.traj_infos_queue = _mp.Queue()
-        self.sync = AttrDict(obs_ready=[_mp.Semaphore(0) for _ in range(n_worker)],
-                             act_ready=[_mp.Semaphore(0) for _ in range(n_worker)])
+        # step-loop handshakes: futex semaphores as in the reference (default), or the spinning
+        # single-producer/single-consumer counters of utils/synchronize.py (RLPYT_B200_SAMPLER_SPIN=1:
+        # 11 us instead of 150 us per 7-worker round trip on the build host; off by default until it has
+        # run the GPU sampler tests - DESIGN.md section 6)
+        if os.environ.get("RLPYT_B200_SAMPLER_SPIN", "0") == "1":
+            make_sem = lambda: SpinSemaphore(_mp)
+        else:
+            make_sem = lambda: _mp.Semaphore(0)
+        self.sync = AttrDict(obs_ready=[make_sem() for _ in range(n_worker)],
+                             act_ready=[make_sem() for _ in range(n_worker)])
         if traj_info_kwargs:
             for k, v in traj_info_kwargs.items():
                 setattr(self.TrajInfoCls, "_" + k, v)

@@ -24,3 +24,66 @@ def drain_queue(queue_obj, n_sentinel=0, guard_sentinel=False):
             return contents
         if obj is not None:
             contents.append(obj)
+
+
+class SpinSemaphore:
+    """Single-producer / single-consumer counting semaphore in fork-shared memory that is waited on by
+    SPINNING instead of sleeping on a futex (``multiprocessing.Semaphore``): a release is one store,
+    an acquire sees it within a cache-line transfer, where a futex wake-up costs tens of microseconds
+    of scheduler latency - twice per environment step per worker in the sampler's step loop
+    (rlpyt/samplers/parallel/gpu/action_server.py:37-62 pairs every step with 2 x n_worker semaphore
+    operations).  Same ``acquire() / acquire(block=False) / release()`` surface as the semaphores it
+    replaces; exactly one process may release and exactly one may acquire a given instance.
+
+    Correctness on x86-64 (TSO): ``posted`` is written only by the releaser and ``taken`` only by the
+    acquirer, so no atomic read-modify-write is needed; stores become visible in program order, and the
+    non-temporal observation stores of ``rl_host_stream_copy`` are followed by ``sfence`` before the
+    counter is bumped.  A waiter that has spun for ``nap_after`` seconds starts napping between polls
+    (a peer that is gone must not burn a core forever)."""
+
+    def __init__(self, ctx=None, nap_after=2.0):
+        import multiprocessing as mp
+        ctx = ctx or mp
+        # two counters on separate cache lines (8 x int64 = 64 B apart)
+        self._raw = ctx.RawArray("q", 16)
+        self._nap_after = nap_after
+
+    def _view(self):
+        import numpy as np
+        v = getattr(self, "_np", None)
+        if v is None:
+            v = self._np = np.frombuffer(self._raw, dtype=np.int64)
+        return v
+
+    def __getstate__(self):          # the numpy view is rebuilt lazily in the child / after pickling
+        return {"_raw": self._raw, "_nap_after": self._nap_after}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    def release(self):
+        v = self._view()
+        v[0] += 1                    # posted
+
+    def acquire(self, block=True, timeout=None):
+        import time
+        v = self._view()
+        taken = v[8]
+        if v[0] > taken:
+            v[8] = taken + 1
+            return True
+        if not block:
+            return False
+        t0 = time.perf_counter()
+        deadline = None if timeout is None else t0 + timeout
+        spins = 0
+        while v[0] <= taken:
+            spins += 1
+            if spins & 0xFFF == 0:
+                now = time.perf_counter()
+                if deadline is not None and now > deadline:
+                    return False
+                if now - t0 > self._nap_after:
+                    time.sleep(0.0005)
+        v[8] = taken + 1
+        return True
