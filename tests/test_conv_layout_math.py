@@ -140,3 +140,58 @@ def test_wgrad_position_walk_matches_division():
                     while oy >= OH:
                         oy -= OH
                         n += 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# Planned v2 formulation (DESIGN.md section 6): space-to-depth turns both strided convolutions into
+# 2x2 stride-1 convolutions over 64 channels, so the four taps are four ROW-SHIFTED views of one operand
+# tile (shifted tcgen05 descriptors) and every input element is converted / written to shared memory
+# once instead of four times.  These tests pin the identities the kernels will rely on.
+def space_to_depth(x, s, pad):
+    """[N,C,H,W] -> X[N, Y*GW + X, (c, ky', kx')] with Y = (H + 2 pad)/s rows of the padded grid."""
+    N, C, H, W = x.shape
+    xp = F.pad(x, (pad, pad, pad, pad))
+    GH, GW = (H + 2 * pad) // s, (W + 2 * pad) // s
+    xp = xp[:, :, :GH * s, :GW * s].reshape(N, C, GH, s, GW, s)
+    return xp.permute(0, 2, 4, 1, 3, 5).reshape(N, GH * GW, C * s * s), GH, GW
+
+
+@pytest.mark.parametrize("geom", [dict(C=4, OC=16, k=8, s=4, p=0, H=84, W=84), dict(C=16, OC=32, k=4, s=2, p=1, H=20, W=20),
+                                  dict(C=4, OC=16, k=8, s=4, p=0, H=104, W=80)])
+def test_space_to_depth_shifted_gemm(geom):
+    g = torch.Generator().manual_seed(2)
+    C, OC, k, s, p, H, W = (geom[n] for n in "C OC k s p H W".split())
+    N = 2
+    x = torch.randn(N, C, H, W, dtype=torch.float64, generator=g)
+    w = torch.randn(OC, C, k, k, dtype=torch.float64, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, stride=s, padding=p)
+    OH, OW = y.shape[2:]
+    X, GH, GW = space_to_depth(x, s, p)                               # [N, GH*GW, 64]
+    assert X.shape[2] == 64 and GH >= OH + 1 and GW >= OW + 1
+    # W4[(by,bx)][oc, (c,ky',kx')] = w[oc, c, s*by+ky', s*bx+kx']
+    W4 = w.detach().reshape(OC, C, 2, s, 2, s).permute(2, 4, 0, 1, 3, 5).reshape(2, 2, OC, C * s * s)
+    flat = X.reshape(N * GH * GW, 64)                                 # images back to back, as in HBM
+    rows = torch.arange(N * GH * GW)
+    Y = torch.zeros(N * GH * GW, OC, dtype=torch.float64)
+    for by in range(2):
+        for bx in range(2):
+            shift = by * GW + bx                                      # the descriptor row offset of this tap
+            src = torch.clamp(rows + shift, max=N * GH * GW - 1)      # rows past the end feed discarded outputs only
+            Y += flat[src] @ W4[by, bx].T
+    Yg = Y.reshape(N, GH, GW, OC)[:, :OH, :OW].permute(0, 3, 1, 2)     # valid grid positions only
+    np.testing.assert_allclose(Yg.numpy(), y.detach().numpy(), rtol=1e-11, atol=1e-11)
+    # weight gradient with the SMALL operand shifted instead: D[(by,bx)][ch, oc] = sum_pos X[pos, ch] * G[pos - shift, oc]
+    go = torch.randn(y.shape, dtype=torch.float64, generator=g)
+    y.backward(go)
+    Gg = torch.zeros(N, GH, GW, OC, dtype=torch.float64)
+    Gg[:, :OH, :OW] = go.permute(0, 2, 3, 1)                           # zero on the invalid last row / column
+    Gf = Gg.reshape(N * GH * GW, OC)
+    dW4 = torch.zeros(2, 2, OC, C * s * s, dtype=torch.float64)
+    for by in range(2):
+        for bx in range(2):
+            shift = by * GW + bx
+            Gs = torch.zeros_like(Gf)
+            Gs[shift:] = Gf[:Gf.shape[0] - shift] if shift else Gf
+            dW4[by, bx] = (flat.T @ Gs).T
+    dW = dW4.reshape(2, 2, OC, C, s, s).permute(2, 3, 0, 4, 1, 5).reshape(w.shape)
+    np.testing.assert_allclose(dW.numpy(), w.grad.numpy(), rtol=1e-10, atol=1e-10)
