@@ -195,3 +195,60 @@ def test_space_to_depth_shifted_gemm(geom):
             dW4[by, bx] = (flat.T @ Gs).T
     dW = dW4.reshape(2, 2, OC, C, s, s).permute(2, 3, 0, 4, 1, 5).reshape(w.shape)
     np.testing.assert_allclose(dW.numpy(), w.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_v2_probe_index_mappings():
+    """Thread-level emulation of tools/probes/conv1_v2_probe.cu (items -> stage rows/chunks, filter-bank
+    tiles, shifted tap reads, epilogue decode) against torch's convolution - everything of the probe
+    except the hardware descriptor semantics, which only the GPU run can answer."""
+    N, H, W = 3, 84, 84
+    GH, GW, OH, OW = H // 4, W // 4, 20, 20
+    G, g_total = GH * GW, N * GH * GW
+    kRows, kStageRows, kProd = 128, 160, 256
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, (N, 4, H, W), dtype=torch.uint8, generator=gen)
+    w = torch.randn(16, 4, 8, 8, dtype=torch.float64, generator=gen) / 8
+    b = torch.randn(16, dtype=torch.float64, generator=gen)
+    xf = x.reshape(-1).numpy()
+    # filter bank tiles: Bt[tap][kb][oc][32]
+    Bt = np.zeros((4, 2, 16, 32))
+    for idx in range(4 * 2 * 16 * 8):
+        j, oc, kb, tap = idx & 7, (idx >> 3) & 15, (idx >> 7) & 1, idx >> 8
+        by, bx = tap >> 1, tap & 1
+        ch0 = kb * 32 + j * 4
+        c, kyp = ch0 >> 4, (ch0 >> 2) & 3
+        Bt[tap, kb, oc, 4 * j:4 * j + 4] = w[oc, c, 4 * by + kyp, 4 * bx:4 * bx + 4].numpy()
+    out = np.full((N, 16, OH, OW), np.nan)
+    for tile in range((g_total + kRows - 1) // kRows):
+        # row table (one decode per stage row)
+        row_off = np.full(kStageRows, -1, dtype=np.int64)
+        for p in range(kStageRows):
+            gg = tile * kRows + p
+            if gg < g_total:
+                n, pos = divmod(gg, G)
+                Yg, Xg = divmod(pos, GW)
+                row_off[p] = n * 4 * H * W + 4 * Yg * W + 4 * Xg
+        stage = np.zeros((2, kStageRows, 32))
+        for tid in range(kProd):
+            for i in range(kStageRows * 16 // kProd):
+                item = tid + i * kProd
+                p, q = item % kStageRows, item // kStageRows
+                c, kyp = q >> 2, q & 3
+                if row_off[p] >= 0:
+                    a = row_off[p] + (c * H + kyp) * W
+                    stage[q >> 3, p, 4 * (q & 7):4 * (q & 7) + 4] = xf[a:a + 4]
+        acc = np.zeros((2, kRows, 16))
+        for tap in range(4):
+            shift = (tap >> 1) * GW + (tap & 1)
+            for kb in range(2):
+                acc[tap >> 1] += stage[kb, shift:shift + kRows] @ Bt[tap, kb].T
+        for i in range(kRows):
+            gg = tile * kRows + i
+            if gg < g_total:
+                n, pos = divmod(gg, G)
+                Yg, Xg = divmod(pos, GW)
+                if Yg < OH and Xg < OW:
+                    out[n, :, Yg, Xg] = np.maximum((acc[0, i] + acc[1, i]) / 255.0 + b.numpy(), 0)
+    ref = F.relu(F.conv2d(x.double() / 255, w, b, stride=4)).numpy()
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-10)
