@@ -252,3 +252,60 @@ def test_v2_probe_index_mappings():
     ref = F.relu(F.conv2d(x.double() / 255, w, b, stride=4)).numpy()
     assert not np.isnan(out).any()
     np.testing.assert_allclose(out, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_wgrad_v2_probe_index_mappings():
+    """Thread-level emulation of tools/probes/conv1_wgrad_v2_probe.cu: K-block = grid row, A^T units (four
+    words -> four transposed chunks), G units written aligned (bx = 0) and one element to the right (bx = 1),
+    the [64 ch x 64 (tap, oc)] accumulator and the reduce kernel's scatter into the [16,4,8,8] gradient."""
+    N, H, W = 2, 84, 84
+    GH, GW, OH, OW = H // 4, W // 4, 20, 20
+    n16, nG, P = (GW + 3) // 4, (OW + 3) // 4, OH * OW
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randint(0, 256, (N, 4, H, W), dtype=torch.uint8, generator=gen)
+    w = torch.zeros(16, 4, 8, 8, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(16, dtype=torch.float64, requires_grad=True)
+    out = torch.randn(N, 16, OH, OW, dtype=torch.float64, generator=gen)
+    go = torch.randn(N, 16, OH, OW, dtype=torch.float64, generator=gen)
+    gm = go * (out > 0)
+    F.conv2d(x.double() / 255, w, b, stride=4).backward(gm)
+    xf, gf, of = x.reshape(-1).numpy(), go.reshape(-1).numpy(), out.reshape(-1).numpy()
+    D = np.zeros((64, 64))
+    bias = np.zeros(16)
+    for kb in range(N * GH):
+        n, Yg = divmod(kb, GH)
+        At = np.zeros((64, 32))
+        Bt = np.zeros((64, 32))
+        for tid in range(16 * n16):                                   # A^T units
+            a_c, a_ky, a_j = tid // (4 * n16), (tid // n16) & 3, tid % n16
+            words = min(4, (W - a_j * 16) // 4)
+            base = n * 4 * H * W + (a_c * H + 4 * Yg + a_ky) * W + a_j * 16
+            for pos in range(words):
+                for kx in range(4):
+                    At[a_c * 16 + a_ky * 4 + kx, 4 * a_j + pos] = xf[base + 4 * pos + kx]
+        for gt in range(32 * nG):                                     # G units
+            g_row, g_j = divmod(gt, nG)
+            g_oc, g_by = g_row & 15, (g_row >> 4) & 1
+            oy = Yg - g_by
+            e = np.zeros(4)
+            if 0 <= oy < OH:
+                base = (n * 16 + g_oc) * P + oy * OW + 4 * g_j
+                for t in range(4):
+                    if 4 * g_j + t < OW:
+                        e[t] = gf[base + t] if of[base + t] > 0 else 0.0
+            if g_by == 0:
+                bias[g_oc] += e.sum()
+            row0 = (g_by * 2) * 16 + g_oc
+            Bt[row0, 4 * g_j:4 * g_j + 4] = e
+            for t in range(4):
+                Bt[row0 + 16, 4 * g_j + t + 1] = e[t]
+        D += At @ Bt.T
+    dW = np.zeros((16, 4, 8, 8))
+    for i in range(64 * 64):                                          # wgrad_v2_reduce_kernel
+        ch, col = i >> 6, i & 63
+        tap, oc = col >> 4, col & 15
+        by, bx = tap >> 1, tap & 1
+        c, kyp, kxp = ch >> 4, (ch >> 2) & 3, ch & 3
+        dW[oc, c, 4 * by + kyp, 4 * bx + kxp] = D[ch, col] / 255.0
+    np.testing.assert_allclose(dW, w.grad.numpy(), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(bias, b.grad.numpy(), rtol=1e-10, atol=1e-10)
