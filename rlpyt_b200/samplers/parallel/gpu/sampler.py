@@ -26,7 +26,7 @@ from rlpyt_b200.samplers.collectors import GpuResetCollector
 from rlpyt_b200.samplers.rollout import DeviceRollout
 from rlpyt_b200.utils.collections import AttrDict
 from rlpyt_b200.utils.seed import set_seed, set_envs_seeds
-from rlpyt_b200.utils.synchronize import drain_queue, SpinSemaphore
+from rlpyt_b200.utils.synchronize import drain_queue, SpinSemaphore, SpinThenSleepSemaphore
 
 _mp = mp.get_context("fork")
 
@@ -106,14 +106,21 @@ class GpuSampler(BaseSampler):
             itr=_mp.RawValue(ctypes.c_long, 0),
         )
         self.traj_infos_queue = _mp.Queue()
-        # step-loop handshakes: futex semaphores as in the reference (default), or the spinning
-        # single-producer/single-consumer counters of utils/synchronize.py (RLPYT_B200_SAMPLER_SPIN=1:
-        # 11 us instead of 150 us per 7-worker round trip on the build host; off by default until it has
-        # run the GPU sampler tests - DESIGN.md section 6)
-        if os.environ.get("RLPYT_B200_SAMPLER_SPIN", "0") == "1":
+        # step-loop handshakes (RLPYT_B200_SAMPLER_SYNC): "futex" = multiprocessing semaphores as in the
+        # reference (default); "spin" = spinning single-producer/single-consumer counters; "hybrid" = the
+        # same semaphores behind a bounded spin (utils/synchronize.py).  On the build host a 7-worker
+        # round trip costs 330 us / 9 us / 19 us; the non-default modes stay opt-in until they have been
+        # measured on the GPU box - tests/test_sampler_protocol_cpu.py runs the
+        # real worker loop against all three.
+        mode = os.environ.get("RLPYT_B200_SAMPLER_SYNC", "futex")
+        if mode == "spin":
             make_sem = lambda: SpinSemaphore(_mp)
-        else:
+        elif mode == "hybrid":
+            make_sem = lambda: SpinThenSleepSemaphore(_mp)
+        elif mode == "futex":
             make_sem = lambda: _mp.Semaphore(0)
+        else:
+            raise ValueError(f"RLPYT_B200_SAMPLER_SYNC must be futex, spin or hybrid (got {mode!r})")
         self.sync = AttrDict(obs_ready=[make_sem() for _ in range(n_worker)],
                              act_ready=[make_sem() for _ in range(n_worker)])
         if traj_info_kwargs:
