@@ -33,7 +33,7 @@ constexpr int kStageBytes = kATile + 2 * kBTile;   // A | G hi | G lo = 32 KiB
 constexpr int kStages = 4, kPromote = 8;
 constexpr int kN = 64;                      // (tap, oc)
 constexpr int kTmemCols = 128;              // 2 buffers x 64 columns
-constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024 + 1024 * 8;   // + row table
 constexpr int kDepthA = 3, kDepthG = 2;
 
 struct Geom {
@@ -43,9 +43,14 @@ struct Geom {
     int n_slices;                           // K slices (8 positions) that hold valid positions = ceil(GW / 8)
 };
 
+// kRowMode 0: images in order; 1: minibatch row indices (rows[n] = image of sample n), this CTA's slice staged in
+// shared memory so that the fetch loop has no dependent global load (see conv_tc.cu, kRowMode).
+constexpr int kRowTab = 1024;
+
+template <int kRowMode>
 __global__ void __launch_bounds__(kThreads, 1)
-conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const float* __restrict__ Out, const float* __restrict__ Gr,
-                      float* __restrict__ partial, float* __restrict__ partial_bias, Geom g) {
+conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const int64_t* __restrict__ rows, const float* __restrict__ Out,
+                      const float* __restrict__ Gr, float* __restrict__ partial, float* __restrict__ partial_bias, Geom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -54,6 +59,7 @@ conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const float* __restrict__ O
     uint64_t* acc_full = bars + 2 * kStages;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int64_t* row_tab = reinterpret_cast<int64_t*>(smem + kStages * kStageBytes + 256);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     constexpr uint32_t kIdesc = make_idesc_tf32(128, kN);
 
@@ -64,6 +70,10 @@ conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const float* __restrict__ O
     const int64_t my_kb = kb_end > kb_begin ? kb_end - kb_begin : 0;
     const int64_t num_chunks = (my_kb + kPromote - 1) / kPromote;
 
+    const int64_t n_lo = kb_begin / g.GH;                      // first sample this CTA touches
+    if (kRowMode == 1) {
+        for (int i = threadIdx.x; i < kRowTab; i += kThreads) row_tab[i] = (n_lo + i < g.n_img) ? rows[n_lo + i] : 0;
+    }
     // zero the whole ring once: padding rows / chunks are never written afterwards
     for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,6 +102,7 @@ conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const float* __restrict__ O
     if (warp < 8) {
         // ================================================================ producers
         const uint32_t ring = smem_u32(smem);
+        const uint32_t row_tab_u32 = smem_u32(row_tab);
         const int tid = threadIdx.x;
         // A^T role: unit u = tid < 16 * n16: (c, ky', j16) -> one 16-byte load per K-block
         const bool a_thread = tid < 16 * g.n16;
@@ -117,7 +128,9 @@ conv1_wgrad_v2_kernel(const uint8_t* __restrict__ X, const float* __restrict__ O
             if (!a_thread) return;
             const int64_t n = kb / g.GH;
             const int Yg = static_cast<int>(kb - n * g.GH);
-            const uint8_t* p = X + n * img_bytes + (static_cast<int64_t>(a_c) * g.H + 4 * Yg + a_ky) * g.W + a_j * 16;
+            int64_t img = n;
+            if (kRowMode == 1) img = lds_s64(row_tab_u32 + static_cast<uint32_t>(n - n_lo) * 8u);
+            const uint8_t* p = X + img * img_bytes + (static_cast<int64_t>(a_c) * g.H + 4 * Yg + a_ky) * g.W + a_j * 16;
             // input rows are only 4-byte aligned in general (W = 84): four word loads, not one 16-byte load
             const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
             if (a_words > 0) h.v.x = q[0];
@@ -319,15 +332,31 @@ int main(int argc, char** argv) {
     cudaMemcpy(dx, hx.data(), hx.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dg, hg.data(), hg.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dout, ho.data(), ho.size() * 4, cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(w2::conv1_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::kSmemBytes);
+    cudaFuncSetAttribute(w2::conv1_wgrad_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::kSmemBytes);
+    cudaFuncSetAttribute(w2::conv1_wgrad_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::kSmemBytes);
+    // minibatch row indices: a permutation of the images (sample n reads image hrows[n])
+    std::vector<int64_t> hrows(N);
+    for (int i = 0; i < N; ++i) hrows[i] = i;
+    for (int i = N - 1; i > 0; --i) { const int j = rnd() % (i + 1); std::swap(hrows[i], hrows[j]); }
+    int64_t* drows;
+    cudaMalloc(&drows, static_cast<size_t>(N) * 8);
+    cudaMemcpy(drows, hrows.data(), static_cast<size_t>(N) * 8, cudaMemcpyHostToDevice);
+    int use_rows = 0;
     auto launch = [&](int n_img) {
         w2::Geom gg = g;
         gg.n_img = n_img;
         const int64_t total_kb = static_cast<int64_t>(n_img) * g.GH;
         const unsigned grid = static_cast<unsigned>(total_kb < sms ? total_kb : sms);
-        w2::conv1_wgrad_v2_kernel<<<grid, w2::kThreads, w2::kSmemBytes>>>(dx, dout, dg, dpart, dpb, gg);
+        const int64_t per_cta = (total_kb + grid - 1) / grid;
+        if (per_cta / g.GH + 2 > w2::kRowTab) { printf("row table too small\n"); exit(1); }
+        if (use_rows)
+            w2::conv1_wgrad_v2_kernel<1><<<grid, w2::kThreads, w2::kSmemBytes>>>(dx, drows, dout, dg, dpart, dpb, gg);
+        else
+            w2::conv1_wgrad_v2_kernel<0><<<grid, w2::kThreads, w2::kSmemBytes>>>(dx, nullptr, dout, dg, dpart, dpb, gg);
         w2::wgrad_v2_reduce_kernel<<<16, 256>>>(dpart, dpb, static_cast<int>(grid), dw, db);
     };
+    cudaEvent_t e0, e1;
+    for (use_rows = 0; use_rows < 2; ++use_rows) {
     // ---- correctness on the first n_chk images against fp64 loops
     const int n_chk = N < 48 ? N : 48;
     launch(n_chk);
@@ -348,7 +377,7 @@ int main(int argc, char** argv) {
                     for (int c = 0; c < 4; ++c)
                         for (int ky = 0; ky < 8; ++ky)
                             for (int kx = 0; kx < 8; ++kx) {
-                                const double a = hx[((static_cast<size_t>(n) * 4 + c) * H + 4 * oy + ky) * W + 4 * ox + kx] / 255.0;
+                                const double a = hx[((static_cast<size_t>(use_rows ? hrows[n] : n) * 4 + c) * H + 4 * oy + ky) * W + 4 * ox + kx] / 255.0;
                                 rw[((oc * 4 + c) * 8 + ky) * 8 + kx] += a * gv;
                                 rws[((oc * 4 + c) * 8 + ky) * 8 + kx] += std::fabs(a * gv);
                             }
@@ -357,10 +386,9 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 1024; ++i) worst = std::fmax(worst, std::fabs(gw[i] - rw[i]) / (rws[i] + 1e-30));
     double worst_b = 0.0;
     for (int i = 0; i < 16; ++i) worst_b = std::fmax(worst_b, std::fabs(gb[i] - rb[i]) / (rbs[i] + 1e-30));
-    printf("n_chk=%d  dW max err / term scale = %.3e, db = %.3e -> %s\n", n_chk, worst, worst_b,
+    printf("rows=%d n_chk=%d  dW max err / term scale = %.3e, db = %.3e -> %s\n", use_rows, n_chk, worst, worst_b,
            (worst <= 1e-5 && worst_b <= 1e-5) ? "OK" : "MISMATCH");
     // ---- timing at full size
-    cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) launch(N);
     cudaEventRecord(e0);
@@ -372,5 +400,6 @@ int main(int argc, char** argv) {
     e = cudaGetLastError();
     printf("conv1 wgrad v2: %.1f us per launch at N=%d (v1 tcgen05 kernel: ~780 us at N=8192) %s\n", ms * 100.0f, N,
            e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
     return 0;
 }
