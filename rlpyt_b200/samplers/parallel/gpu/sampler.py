@@ -23,6 +23,7 @@ import torch
 from rlpyt_b200.samplers.base import BaseSampler
 from rlpyt_b200.samplers.buffer import build_samples_buffer, pin_shared, unpin_shared, StepBuffer
 from rlpyt_b200.samplers.collectors import GpuResetCollector
+from rlpyt_b200.samplers.eval_collector import build_eval_collector
 from rlpyt_b200.samplers.rollout import DeviceRollout
 from rlpyt_b200.utils.collections import AttrDict
 from rlpyt_b200.utils.seed import set_seed, set_envs_seeds
@@ -160,6 +161,7 @@ class GpuSampler(BaseSampler):
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)
         self.samples_pyt = self.samples
+        self.eval_collector = build_eval_collector(self, agent, seed)     # after the fork: master-only envs
         return examples
 
     def obtain_samples(self, itr):
@@ -173,7 +175,11 @@ class GpuSampler(BaseSampler):
         return self.samples, traj_infos
 
     def evaluate_agent(self, itr):
-        raise NotImplementedError("offline evaluation collectors are outside the accelerated path")
+        """Evaluation runs in the master process (samplers/eval_collector.py): the training step loop
+        and its worker protocol stay untouched."""
+        if self.eval_collector is None:
+            raise RuntimeError("evaluate_agent needs eval_n_envs > 0 (and eval_max_steps) at construction")
+        return self.eval_collector.collect_evaluation(itr)
 
     def shutdown(self):
         self.ctrl.quit.value = True

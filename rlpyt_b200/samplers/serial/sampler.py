@@ -8,6 +8,7 @@ import torch
 from rlpyt_b200.samplers.base import BaseSampler
 from rlpyt_b200.samplers.buffer import build_samples_buffer
 from rlpyt_b200.samplers.collectors import DecorrelatingStartCollector
+from rlpyt_b200.samplers.eval_collector import build_eval_collector
 from rlpyt_b200.samplers.rollout import DeviceRollout
 from rlpyt_b200.utils.seed import set_envs_seeds
 
@@ -43,6 +44,7 @@ class SerialSampler(BaseSampler):
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)
         self.samples_pyt = self.samples
+        self.eval_collector = build_eval_collector(self, agent, seed)
         return examples
 
     def obtain_samples(self, itr):
@@ -73,4 +75,7 @@ class SerialSampler(BaseSampler):
         return self.samples, completed
 
     def evaluate_agent(self, itr):
-        raise NotImplementedError("offline evaluation collectors are outside the accelerated path")
+        """serial/sampler.py:107-109."""
+        if self.eval_collector is None:
+            raise RuntimeError("evaluate_agent needs eval_n_envs > 0 (and eval_max_steps) at construction")
+        return self.eval_collector.collect_evaluation(itr)
