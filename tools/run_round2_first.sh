@@ -19,3 +19,19 @@ RLPYT_B200_SAMPLER_SYNC=hybrid timeout 600 python -m pytest tests/test_gpu_sampl
 RLPYT_B200_SAMPLER_SYNC=spin timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q 2>&1 | tail -3
 # 3. DQN learner benchmark (parity-green in round 1, unmeasured)
 timeout 600 python tools/bench_dqn.py > $OUT/bench_dqn.json 2> $OUT/bench_dqn.err; tail -2 $OUT/bench_dqn.err; cut -c1-700 $OUT/bench_dqn.json
+# 4. evaluate_agent (added at the end of round 1, CPU-tested only): one evaluation through the GpuSampler
+timeout 300 python - <<'PY' 2>&1 | tail -3
+import torch
+from rlpyt_b200.agents.pg.atari import AtariFfAgent
+from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
+from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
+kw = dict(image_shape=(4, 84, 84), n_actions=6, p_done=0.05)
+s = GpuSampler(EnvCls=SyntheticAtariEnv, env_kwargs=kw, batch_T=8, batch_B=8, max_decorrelation_steps=0,
+               eval_n_envs=4, eval_max_steps=400, eval_max_trajectories=10)
+agent = AtariFfAgent()
+s.initialize(agent, affinity=dict(cuda_idx=0, workers_cpus=[0, 1]), seed=0, bootstrap_value=True)
+infos = s.evaluate_agent(itr=1)
+print("evaluate_agent:", len(infos), "trajectories, mean length", sum(i.Length for i in infos) / max(1, len(infos)))
+s.obtain_samples(0)
+s.shutdown()
+PY
