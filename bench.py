@@ -126,7 +126,10 @@ def run_b200(args):
     seed = 0 + 100 * rank                                            # sync_rl.py:82 seeds per rank
     np.random.seed(seed)
     torch.manual_seed(seed)
-    sampler = GpuSampler(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
+    SamplerCls = GpuSampler
+    if os.environ.get("RLPYT_B200_BENCH_SAMPLER", "gpu") == "alternating":   # experimental
+        from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler as SamplerCls
+    sampler = SamplerCls(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
                          max_decorrelation_steps=20)
     agent = AtariFfAgent()
     from rlpyt_b200.utils.affinity import make_affinity

@@ -1,0 +1,102 @@
+"""Alternating GPU sampler (mirror of ``rlpyt/samplers/parallel/gpu/alternating_sampler.py:8-85`` with the
+step protocol of ``AlternatingActionServer``, ``rlpyt/samplers/parallel/gpu/action_server.py:123-173``;
+SURVEY.md section 8(f) row 3): the workers form two groups, each owning half of the environments; while one
+group steps its envs the master uploads, acts and records for the other group, so the GPU part of a step
+(H2D + ``agent.step`` + D2H, ~0.35 ms) leaves the critical path when env stepping takes at least as long.
+
+Built from the pieces of ``GpuSampler``: the same forked ``sampling_process`` workers and collectors, and
+one ``DeviceRollout`` step engine per half operating on B-axis views of the same ``[T,B]`` HBM buffers and
+of the pinned step buffer (each half replays its own per-step CUDA graphs).  Feed-forward agents only (the
+recurrent alternating agents of the reference are outside the accelerated path).
+
+Status: written at the end of round 1 after the GPU budget was spent; the worker side is the protocol
+tested in tests/test_sampler_protocol_cpu.py, the master side has NOT run on a GPU yet
+(tools/run_round2_first.sh exercises it).
+"""
+import numpy as np
+import torch
+
+from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
+from rlpyt_b200.samplers.rollout import DeviceRollout
+
+
+class AlternatingSampler(GpuSampler):
+
+    alternating = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert self.batch_spec.B % 2 == 0, "Need even number for sampler batch_B."
+
+    def initialize(self, agent, *args, **kwargs):
+        if getattr(agent, "recurrent", False):
+            raise NotImplementedError("recurrent alternating agents are outside the accelerated path")
+        agent.alternating = True           # alternating_sampler.py:37: a feed-forward agent only needs the flag
+        examples = super().initialize(agent, *args, **kwargs)
+        self._make_alternating_pairs()
+        return examples
+
+    def _get_n_envs_list(self, n_worker):
+        """Even number of workers, the two halves mirror each other (alternating_sampler.py:64-80)."""
+        B = self.batch_spec.B
+        n_worker = min(n_worker, B) // 2 * 2
+        if n_worker < 2:
+            raise ValueError("AlternatingSampler needs at least 2 workers (affinity['workers_cpus'])")
+        n_envs_list = [B // n_worker] * n_worker
+        for w in range((B % n_worker) // 2):
+            n_envs_list[w] += 1
+            n_envs_list[w + n_worker // 2] += 1
+        assert sum(n_envs_list) == B and sum(n_envs_list[:n_worker // 2]) == B // 2
+        return n_envs_list
+
+    def _make_alternating_pairs(self):
+        half_w, B = self.n_worker // 2, self.batch_spec.B
+        half_B = B // 2
+        assert self.worker_slices[half_w].start == half_B
+        self.halves = (slice(0, half_B), slice(half_B, B))
+        self.obs_ready_pair = (self.sync.obs_ready[:half_w], self.sync.obs_ready[half_w:])
+        self.act_ready_pair = (self.sync.act_ready[:half_w], self.sync.act_ready[half_w:])
+        host = self.host
+        self.rollouts = []
+        for sl in self.halves:
+            host_h = dict(step_np=host["step_np"][sl], step_pyt=host["step_pyt"][sl],
+                          all_action=host["all_action"][:, sl], all_reward=host["all_reward"][:, sl])
+            ro = DeviceRollout(self.samples[:, sl], host_h, self.agent, self.device)
+            ro.in_action.copy_(host_h["step_pyt"].action)
+            self.rollouts.append(ro)
+
+    def serve_actions(self, itr):
+        """action_server.py:131-173 on the device step engines."""
+        T = self.batch_spec.T
+        wait_reset = not self.mid_batch_reset
+        for t in range(T):
+            for alt in range(2):
+                ro, sl = self.rollouts[alt], self.halves[alt]
+                for s in self.obs_ready_pair[alt]:
+                    s.acquire()                              # this half wrote obs(t), reward(t-1), done(t-1)
+                done_now = ro.step_np.done
+                if self.mid_batch_reset and np.any(done_now):
+                    for b in np.where(done_now)[0]:
+                        self.agent.reset_one(idx=int(b) + sl.start)
+                ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
+                for s in self.act_ready_pair[alt]:
+                    s.release()                              # this half steps while the other is served
+        for alt in range(2):
+            ro, sl = self.rollouts[alt], self.halves[alt]
+            for s in self.obs_ready_pair[alt]:
+                s.acquire()
+            ro.finish()                                      # bootstrap value of this half
+            if np.any(ro.step_np.done):
+                ended = np.where(ro.step_np.done)[0]
+                ro.step_np.action[ended] = 0
+                ro.step_np.reward[ended] = 0
+                for b in ended:
+                    self.agent.reset_one(idx=int(b) + sl.start)
+                ro.zero_inputs_where_done()
+        torch.cuda.current_stream(self.device).synchronize()
+        for ro in self.rollouts:
+            ro.end_batch()
+        for s in self.sync.obs_ready:
+            assert not s.acquire(block=False)                # drained (action_server.py:170-173)
+        for s in self.sync.act_ready:
+            assert not s.acquire(block=False)

@@ -15,6 +15,9 @@ for mode in futex hybrid spin; do
   RLPYT_B200_SAMPLER_SYNC=$mode timeout 300 python bench.py --no-cpu-baseline > $OUT/bench_sync_$mode.json 2> $OUT/bench_sync_$mode.err
   python -c "import json;d=json.load(open('$OUT/bench_sync_$mode.json'));print('$mode', d['value'], d['e2e'])"
 done
+# 2b. alternating sampler (master side never run on a GPU yet)
+RLPYT_B200_BENCH_SAMPLER=alternating timeout 300 python bench.py --no-cpu-baseline > $OUT/bench_alternating.json 2> $OUT/bench_alternating.err
+tail -3 $OUT/bench_alternating.err; python -c "import json;d=json.load(open('$OUT/bench_alternating.json'));print('alternating', d['value'], d['e2e'])"
 RLPYT_B200_SAMPLER_SYNC=hybrid timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q 2>&1 | tail -3
 RLPYT_B200_SAMPLER_SYNC=spin timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q 2>&1 | tail -3
 # 3. DQN learner benchmark (parity-green in round 1, unmeasured)
