@@ -9,9 +9,10 @@ one ``DeviceRollout`` step engine per half operating on B-axis views of the same
 of the pinned step buffer (each half replays its own per-step CUDA graphs).  Feed-forward agents only (the
 recurrent alternating agents of the reference are outside the accelerated path).
 
-Status: written at the end of round 1 after the GPU budget was spent; the worker side is the protocol
-tested in tests/test_sampler_protocol_cpu.py, the master side has NOT run on a GPU yet
-(tools/run_round2_first.sh exercises it).
+Status: written at the end of round 1 after the GPU budget was spent.  tests/test_sampler_protocol_cpu.py
+runs ``serve_actions`` of this class against the real forked worker loop with a stand-in step engine
+(alternation order, drained handshakes, observation streams equal to a host replay); the wiring of the two
+``DeviceRollout`` engines in ``initialize`` has NOT run on a GPU yet (tools/run_round2_first.sh exercises it).
 """
 import numpy as np
 import torch
@@ -93,7 +94,8 @@ class AlternatingSampler(GpuSampler):
                 for b in ended:
                     self.agent.reset_one(idx=int(b) + sl.start)
                 ro.zero_inputs_where_done()
-        torch.cuda.current_stream(self.device).synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
         for ro in self.rollouts:
             ro.end_batch()
         for s in self.sync.obs_ready:
