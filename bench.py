@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py - the driver's measurement contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ppo|gae|replay|dqn]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
+
+``--workload ppo`` (default) is the driver's contract, BASELINE.json configs[2] (configs[4] at N > 1); ``gae``
+(configs[1]), ``replay`` and ``dqn`` (configs[3]) print the same kind of line for the other configurations
+(tools/workload_benches.py; outputs of a B200 run are kept under profiles/).
 
 Metric (BASELINE.json): env-steps/sec of PPO on Atari-shaped data, [T=128, B=256] per GPU, AtariFf
 agent, the reference's PPO hyper-parameters (rlpyt/experiments/configs/atari/pg/atari_ff_ppo.py:5-16);
 plus the GAE-scan GB/s in ``roofline``.
 
 A "step" is one PPO iteration over one [T,B] batch of synthetic samples:
-  value  - ``algo.optimize_agent`` on a batch already resident in HBM (returns + 4x4 minibatch
-           updates: gather, forward, fused loss, backward, all-reduce, clip+Adam);
+  value  - LEARNER ONLY: ``algo.optimize_agent`` on a batch already resident in HBM (returns + 4x4 minibatch
+           updates: gather, forward, fused loss, backward, all-reduce, clip+Adam).  Compare it with the
+           reference line's ``value`` (its optimize_agent alone), never with a loop that also samples;
   e2e    - the public API loop a user runs: ``sampler.obtain_samples`` (CPU synthetic envs in
            worker processes, per-step H2D of observations from pinned host memory, agent.step on
            the GPU, D2H of actions) followed by ``algo.optimize_agent`` (D2H of the OptInfo rows).
+           This is the metric's number (env-steps/s of PPO); compare it with the reference line's ``e2e``.
 Weak scaling: every rank owns B=256 environments; ``value``/``e2e`` are whole-job aggregates.
 """
 import argparse
@@ -121,19 +127,21 @@ def run_b200(args):
 
     all_cpus = sorted(os.sched_getaffinity(0))
     cores = len(all_cpus)
-    # every GPU gets the same host share at every N: one eighth of the box (an 8-GPU node)
-    n_workers = args.workers or max(1, min(B_CFG, cores // 8 - 2))
     seed = 0 + 100 * rank                                            # sync_rl.py:82 seeds per rank
     np.random.seed(seed)
     torch.manual_seed(seed)
     SamplerCls = GpuSampler
-    if os.environ.get("RLPYT_B200_BENCH_SAMPLER", "gpu") == "alternating":   # experimental
+    if os.environ.get("RLPYT_B200_BENCH_SAMPLER", "gpu") == "alternating":
         from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler as SamplerCls
     sampler = SamplerCls(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
                          max_decorrelation_steps=20)
     agent = AtariFfAgent()
     from rlpyt_b200.utils.affinity import make_affinity
-    affinity = make_affinity(local_rank, n_workers, local_rank=local_rank, ranks_per_node=world, reserve_master=4)
+    # every GPU gets the same host share at every N: one eighth of the box's PHYSICAL cores (an 8-GPU node),
+    # the first of them for the master, one env worker per remaining core (--smt-workers: per hardware thread)
+    affinity = make_affinity(local_rank, args.workers or None, local_rank=local_rank, ranks_per_node=world,
+                             node_share=8, smt_workers=args.smt_workers)
+    n_workers = len(affinity["workers_cpus"])
     sampler.initialize(agent, affinity=affinity, seed=seed + 1, bootstrap_value=True, world_size=world, rank=rank)
     agent.to_device(local_rank)
     if world > 1:
@@ -188,6 +196,15 @@ def run_b200(args):
             barrier()
             t_e2e = max_over_ranks(time.perf_counter() - t0)
         e2e = steps_per_itr * K / t_e2e
+        params_identical = None
+        if world > 1:   # data-parallel replicas must hold bit-identical parameters after K+W updates x 16
+            flat = algo.optimizer.flat_param if hasattr(algo.optimizer, "flat_param") else torch.cat(
+                [p.detach().reshape(-1) for p in agent.parameters()])
+            mine = torch.stack([flat.double().sum(), flat.double().abs().sum(),
+                                flat.view(torch.int32).long().sum().double()])
+            allv = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)
+            params_identical = bool(all(torch.equal(v, allv[0]) for v in allv))
         obs_bytes = int(np.prod(IMAGE))
         h2d = (T_CFG + 1) * B_CFG * (obs_bytes + 4 + 1) + 16 * (T_CFG * B_CFG // 4) * 8
         d2h = T_CFG * B_CFG * 8 + 16 * 4 * 4
@@ -203,17 +220,22 @@ def run_b200(args):
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_value / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "value_scope": "learner only: algo.optimize_agent on an HBM-resident [T,B] batch; the metric itself "
+                       "(sampler + learner through the public API, host buffers) is e2e",
         "config": {"workload": "PPO+AtariFfAgent, synthetic Atari env obs (4,84,84) u8, T=128 B=256 per GPU "
                                "(BASELINE.json configs[2]; configs[4] at N>1), gamma .99 lambda .98 lr 1e-3 clip .1 4x4",
                    "global_batch": steps_per_itr, "parallelism": f"dp{world}",
                    "l2": "inputs_larger_than_L2 (925 MB observation batch per rank)",
-                   "env_workers_per_rank": n_workers, "host_cores": cores},
+                   "env_workers_per_rank": n_workers, "host_threads": cores,
+                   "worker_cpus_rank0": [c[0] for c in affinity["workers_cpus"]], "master_cpus_rank0": affinity["master_cpus"]},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / K * 1e3, "sampling_ms_per_step_rank0": t_sample / K * 1e3},
         "gpu_launches": launches,
         "clocks": clk_value.summary(), "clocks_e2e": clk_e2e.summary(),
         "last_opt_info": {k: float(np.mean(getattr(info, k))) for k in info._fields},
     }
+    if params_identical is not None:
+        out["params_identical_across_ranks"] = params_identical
 
     # ---- roofline of the GAE scan kernel at the HBM-bound size, measured live (rank 0)
     if rank == 0:
@@ -316,36 +338,28 @@ def roofline_conv1_wgrad(N=8192, reps=10):
 
 
 def cpu_baseline(U):
-    """The oracle port timed on this box's host cores (rank 0, N=1): (i) one PPO optimize_agent
-    iteration on a bounded [T=128, B=32] sample -> env-steps/s comparable with ``value``;
-    (ii) the north_star unit "reference CPU GAE + PPO-loss" at [128,256] (GAE on torch-CPU tensors +
-    16 x loss fwd+bwd arithmetic at N=8192) next to the same work on the GPU kernels."""
-    from oracle import atari_ff, pg_loss
-    from oracle.ppo import PpoOracle, gae_plus_loss_cpu
+    """Rank 0, N=1: (i) the reference arm (``--impl reference``: the unmodified reference from baseline/_ref on
+    this box's host cores, bounded sample, same config) run as a child process for a few steps - its line's
+    ``value`` (learner only) and ``e2e`` (sampler + learner) are what ``value`` / ``e2e`` above compare with;
+    (ii) the north_star unit "reference CPU GAE + PPO-loss" at [128,256] (GAE on torch-CPU tensors + 16 x loss
+    fwd+bwd arithmetic at N=8192) next to the same work on the GPU kernels."""
+    from oracle import pg_loss  # noqa: F401  (checker side only; see oracle/__init__.py)
+    from oracle.ppo import gae_plus_loss_cpu
     from rlpyt_b200.algos.pg import loss_ops
     threads = torch.get_num_threads()
     rng = np.random.default_rng(0)
-    Tb, Bb = T_CFG, 32
-    obs = rng.integers(0, 256, size=(Tb, Bb) + IMAGE, dtype=np.uint8)
-    action = rng.integers(0, N_ACTIONS, size=(Tb, Bb))
-    reward = rng.choice(np.array([-1, 0, 1], np.float32), size=(Tb, Bb), p=[.02, .96, .02]).astype(np.float32)
-    done = rng.random((Tb, Bb)) < 1 / 500.
-    value = rng.standard_normal((Tb, Bb)).astype(np.float32)
-    prob = rng.dirichlet(np.ones(N_ACTIONS), (Tb, Bb)).astype(np.float32)
-    bv = rng.standard_normal((1, Bb)).astype(np.float32)
-    o = PpoOracle(atari_ff.init_state_dict(IMAGE, N_ACTIONS, 0), n_itr=10 ** 6,
-                  **{k: v for k, v in PPO_KW.items()})
-    o.optimize_agent(0, obs, action, reward, done, value, prob, bv)  # warm-up
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3 and time.perf_counter() - t0 < 15:
-        o.optimize_agent(n + 1, obs, action, reward, done, value, prob, bv)
-        n += 1
-    dt = (time.perf_counter() - t0) / n
-    base = {"value": Tb * Bb / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"oracle/ppo.py PpoOracle.optimize_agent, torch-CPU fp32, {threads} threads, "
-                      f"[T={Tb},B={Bb}] batch ({Tb * Bb} of {T_CFG * B_CFG} env-steps/iteration), {n} iterations",
-            "s_per_iteration_sample": dt}
+    base = {"value": None, "unit": "env-steps/s", "cores": threads, "kind": "reference", "sample": "unavailable"}
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                            "--no-gpu-context"], capture_output=True, text=True, timeout=600,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+        ref = json.loads(line)
+        base = dict(ref["cpu_baseline"])
+        base["e2e_value"] = ref["e2e"]["value"]
+        base["learner_only_value"] = ref["value"]
+    except Exception as e:  # noqa: BLE001 - the baseline must never break the bench line
+        base["error"] = repr(e)[:300]
 
     # (ii) GAE + 16 x PPO-loss, CPU reference arithmetic vs the GPU kernels, full [128,256] size
     T, B, N, A = T_CFG, B_CFG, 8192, N_ACTIONS
@@ -405,19 +419,104 @@ def cpu_baseline(U):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
+REF_T = 16     # bounded sample of the reference arm: [T=16, B=256] per step (B, minibatch structure, env, workers as configured)
+
+
+def _reference_affinity(world):
+    from rlpyt_b200.utils.affinity import make_affinity
+    try:
+        aff = make_affinity(0, None, local_rank=0, ranks_per_node=1, node_share=8)
+        return [c[0] for c in aff["workers_cpus"]]
+    except Exception:  # noqa: BLE001
+        return list(range(max(1, (os.cpu_count() or 2) // 8 - 1)))
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path, as restated by the oracle port (the
-    reference is pure Python and cannot travel to this box): serial CPU rollout + PPO on torch-CPU
-    with all host threads, on a bounded [T=128, B=32] sample per step."""
+    """``--impl reference``: the UNMODIFIED reference (baseline/_ref, installed by the pip recipe in DESIGN.md
+    section 5) through its own API - ``GpuSampler`` with ``cuda_idx=None`` (batched action serving on torch-CPU
+    with every host thread, env stepping in forked workers pinned to the same cores this repo's arm uses) +
+    ``PPO.optimize_agent`` on torch-CPU - baseline/reference_arm.py.  Same config as the b200 arm (B=256, the
+    same PPO hyper-parameters, env and worker cores); each step is a bounded sample [T=16, B=256] of the
+    [T=128, B=256] iteration (4096 of 32768 env-steps: per-env-step cost does not depend on T).
+    ``value`` = learner only (optimize_agent), ``e2e`` = sampler + learner: like for like with the b200 line.
+    Falls back to the oracle port when baseline/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    K, W = args.steps, args.warmup
+    threads = torch.get_num_threads()
+    from baseline import reference_arm as R
+    if not R.available():
+        return run_reference_port(args)
+    workers_cpus = _reference_affinity(1)
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr          # the reference's logger prints to stdout; this arm's stdout is ONE JSON line
+    loop = R.ReferenceLoop(REF_T, B_CFG, ENV_KW, PPO_KW, workers_cpus=workers_cpus, cuda_idx=None, seed=0)
+    try:
+        for _ in range(W):
+            loop.step()
+        loop.reset_timers()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            loop.step()
+        dt = time.perf_counter() - t0
+        t_opt, t_smp = loop.t_optimize, loop.t_sample
+    finally:
+        loop.shutdown()
+    steps = REF_T * B_CFG
+    val_e2e, val_learn = steps * K / dt, steps * K / t_opt
+    sample = (f"unmodified reference (baseline/_ref): GpuSampler(cuda_idx=None, {len(workers_cpus)} worker processes) + "
+              f"PPO on torch-CPU fp32, {threads} threads; bounded sample [T={REF_T},B={B_CFG}] per step "
+              f"({steps} of {T_CFG * B_CFG} env-steps), minibatches=4 epochs=4")
+    out = {
+        "impl": "reference", "metric": "env-steps/sec PPO Atari [T=128,B=256] at 1/2/4/8 GPU; GAE-scan GB/s",
+        "value": val_learn, "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": W,
+        "ms_per_step": t_opt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "value_scope": "learner only: PPO.optimize_agent on torch-CPU (compare with the b200 line's value)",
+        "config": {"workload": "PPO+AtariFfAgent, synthetic Atari env obs (4,84,84) u8, B=256 per GPU, gamma .99 lambda .98 "
+                               "lr 1e-3 clip .1 4x4 (the b200 arm's config)", "sample": sample,
+                   "env_workers": len(workers_cpus)},
+        "cpu_baseline": {"value": val_e2e, "unit": "env-steps/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms_per_step": dt / K * 1e3, "sampling_ms_per_step": t_smp / K * 1e3},
+        "gpu_launches": 0,
+    }
+    # context (SURVEY 8(d) row 3): the same reference objects with cuda_idx=0 = stock PyTorch/cuDNN/cuBLAS on the B200,
+    # full [T=128, B=256] iterations
+    if not args.no_gpu_context and out["n_gpus"] == 1 and torch.cuda.is_available():
+        try:
+            g = R.ReferenceLoop(T_CFG, B_CFG, ENV_KW, PPO_KW, workers_cpus=workers_cpus, cuda_idx=0, seed=0)
+            try:
+                for _ in range(2):
+                    g.step()
+                g.reset_timers()
+                t0 = time.perf_counter()
+                n = 4
+                for _ in range(n):
+                    g.step()
+                gdt = time.perf_counter() - t0
+                out["stock_pytorch_gpu"] = {
+                    "what": "unmodified reference with cuda_idx=0 (stock PyTorch kernels on this B200), [T=128,B=256], "
+                            f"{n} iterations", "e2e_value": T_CFG * B_CFG * n / gdt, "unit": "env-steps/s",
+                    "learner_only_value": T_CFG * B_CFG * n / g.t_optimize, "ms_per_step": gdt / n * 1e3,
+                    "sampling_ms_per_step": g.t_sample / n * 1e3, "optimize_ms_per_step": g.t_optimize / n * 1e3}
+            finally:
+                g.shutdown()
+        except Exception as e:  # noqa: BLE001
+            out["stock_pytorch_gpu"] = {"error": repr(e)[:300]}
+    sys.stdout = real_stdout
+    print(json.dumps(out), flush=True)
+
+
+def run_reference_port(args):
+    """Fallback when baseline/_ref is missing: the oracle port (serial CPU rollout + PPO on torch-CPU)."""
     from oracle import atari_ff
     from oracle.collector import SerialRollout
     from oracle.ppo import PpoOracle
     from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
     threads = torch.get_num_threads()
-    Tb, Bb = T_CFG, 32
+    Tb, Bb = REF_T, B_CFG
     np.random.seed(0)
     torch.manual_seed(0)
     envs = [SyntheticAtariEnv(**ENV_KW) for _ in range(Bb)]
@@ -426,26 +525,31 @@ def run_reference(args):
     sd = atari_ff.init_state_dict(IMAGE, N_ACTIONS, 0)
     algo = PpoOracle(sd, n_itr=10 ** 6, **PPO_KW)
     roll = SerialRollout(envs, sd, Tb, N_ACTIONS)
+    t_opt = [0.0]
 
     def step(itr):
         buf = roll.collect_batch(algo.state_dict())
-        return algo.optimize_agent(itr, buf["observation"], buf["all_action"][1:], buf["all_reward"][1:], buf["done"],
-                                   buf["value"], buf["prob"], buf["bootstrap_value"])
+        t0 = time.perf_counter()
+        r = algo.optimize_agent(itr, buf["observation"], buf["all_action"][1:], buf["all_reward"][1:], buf["done"],
+                                buf["value"], buf["prob"], buf["bootstrap_value"])
+        t_opt[0] += time.perf_counter() - t0
+        return r
     K, W = args.steps, args.warmup
     for i in range(W):
         step(i)
+    t_opt[0] = 0.0
     t0 = time.perf_counter()
     for i in range(K):
         step(W + i)
     dt = time.perf_counter() - t0
     val = Tb * Bb * K / dt
-    sample = (f"oracle port (collector + PPO, torch-CPU fp32, {threads} threads), bounded sample [T={Tb},B={Bb}] "
-              f"per step ({Tb * Bb} of {T_CFG * B_CFG} env-steps)")
+    sample = (f"oracle port (serial collector + PPO, torch-CPU fp32, {threads} threads; baseline/_ref missing), bounded sample "
+              f"[T={Tb},B={Bb}] per step ({Tb * Bb} of {T_CFG * B_CFG} env-steps)")
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec PPO Atari [T=128,B=256] at 1/2/4/8 GPU; GAE-scan GB/s",
-        "value": val, "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": W,
-        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "value": Tb * Bb * K / t_opt[0], "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
+        "warmup": W, "ms_per_step": t_opt[0] / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "value_scope": "learner only (oracle port)",
         "config": {"workload": "PPO+AtariFf on CPU (reference algorithm), synthetic Atari env obs (4,84,84) u8", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -459,9 +563,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--workers", type=int, default=0, help="env workers per rank (0 = one per physical core of the share)")
+    ap.add_argument("--smt-workers", action="store_true", help="one worker per hardware thread instead of per core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-context", action="store_true", help="reference arm: skip the stock-PyTorch-on-GPU context leg")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "gae", "replay", "dqn"])
     args = ap.parse_args()
+    if args.workload != "ppo":
+        from tools import workload_benches
+        return workload_benches.run(args)
     if args.impl == "reference":
         run_reference(args)
     else:

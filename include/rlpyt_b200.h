@@ -236,6 +236,25 @@ int rl_conv1_u8_wgrad_tc(const uint8_t* obs, const int64_t* rows, const float* o
 int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, float* grad_weight,
                       float* grad_bias, int64_t N, int C, int IH, int IW, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ first conv layer on the INTEGER tensor cores
+ * Same contracts as rl_conv1_u8_forward / rl_conv1_u8_wgrad_tc (rlpyt/models/pg/atari_ff_model.py:50-53,
+ * rlpyt/models/conv2d.py:36-44; row gather of rlpyt/algos/pg/ppo.py:99-100), computed with tcgen05.mma kind::i8:
+ * the uint8 frames are exact MMA operands (space-to-depth "cell" rows, no im2col expansion, frames streamed by
+ * cp.async.bulk), the fp32 operand (filter bank / output gradient) is split into four base-128 digits against a
+ * power-of-two scale per output channel, the int32 accumulators are exact and recombined in fp32 (forward) / fp64
+ * (gradient).  Error vs exact arithmetic <= 2^-28 of the channel's largest |weight| (|gradient|) per term.
+ * Requirements: C == 4, H % 4 == 0, W % 4 == 0, W <= 128, frames 16-byte aligned;
+ * rl_conv1_u8_i8_supported() tells whether a geometry fits (else use the *_tc entry points).
+ * wgrad: out may be NULL (grad_out already masked), grad_bias may be NULL; N <= 256 * SM count;
+ * scratch: rl_conv1_u8_wgrad_i8_scratch_bytes() bytes, 16B aligned.  Deterministic. */
+int rl_conv1_u8_i8_supported(int C, int H, int W);
+int rl_conv1_u8_forward_i8(const uint8_t* obs, const int64_t* rows, const float* weight, const float* bias,
+                           float* out, int64_t N, int C, int H, int W, int relu, void* stream);
+int64_t rl_conv1_u8_wgrad_i8_scratch_bytes(void);
+int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                         float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
+                         void* stream);
+
 /* ------------------------------------------------------------------ DQN loss
  * rlpyt/algos/dqn/dqn.py:230-263 `DQN.loss` after the two network forwards: Q(s,a) selection, (double-)DQN
  * target, y = return_ + (1 - done_n) * disc_n * target_q, Huber loss with threshold delta_clip (delta_clip < 0:

@@ -1,8 +1,11 @@
 """``Conv2d(4->16, k8, s4) + ReLU`` on uint8 frames as one autograd op over the hand-written kernels:
 forward (fused with the minibatch row gather and the ``/255`` scaling) and backward (weight and bias
-gradients with the ReLU mask folded in - the input is an observation and needs no gradient) run on the
-tcgen05 kernels of csrc/conv_tc.cu by default; the fp32 SIMT kernels of csrc/conv1.cu remain
-selectable for cross-checks (``RLPYT_B200_CONV1_FWD=simt``, ``RLPYT_B200_CONV_WGRAD=simt``)."""
+gradients with the ReLU mask folded in - the input is an observation and needs no gradient).
+Default implementation "i8": the integer tensor-core kernels of csrc/conv1_i8.cuh (uint8 frames as exact
+``tcgen05.mma kind::i8`` operands, the fp32 operand as four base-128 digits, exact int32 accumulation) whenever
+the geometry fits (H, W multiples of 4, W <= 128); otherwise "tc", the TF32 implicit-GEMM kernels of
+csrc/conv_tc.cu.  ``RLPYT_B200_CONV1_FWD`` / ``RLPYT_B200_CONV_WGRAD`` = i8 | tc | simt select one explicitly
+(simt = the fp32 kernels of csrc/conv1.cu, kept for cross-checks)."""
 import os
 
 import torch
@@ -10,10 +13,29 @@ import torch
 from rlpyt_b200 import _lib
 
 _SCRATCH = {}
-# forward implementation: "tc" = tcgen05 implicit GEMM (csrc/conv_tc.cu), "simt" = fp32 kernel (csrc/conv1.cu)
-FORWARD_IMPL = os.environ.get("RLPYT_B200_CONV1_FWD", "tc")
-# weight gradient: "tc" = tcgen05 GEMM over positions (csrc/conv_tc.cu), "simt" = fp32 kernel (csrc/conv1.cu)
-WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
+FORWARD_IMPL = os.environ.get("RLPYT_B200_CONV1_FWD", "i8")
+WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "i8")
+_I8_OK = {}
+
+
+def i8_supported(C, H, W):
+    key = (C, H, W)
+    if key not in _I8_OK:
+        _I8_OK[key] = bool(_lib.load().rl_conv1_u8_i8_supported(C, H, W))
+    return _I8_OK[key]
+
+
+def _impl(name, C, H, W, N=0):
+    if name == "i8" and not (i8_supported(C, H, W) and N <= 256 * 148):
+        return "tc"
+    return name
+
+
+def _scratch(dev, key, nbytes_fn):
+    k = (str(dev), key)
+    if k not in _SCRATCH:
+        _SCRATCH[k] = torch.empty(int(nbytes_fn()) // 4 + 4, dtype=torch.float32, device=dev)
+    return _SCRATCH[k]
 
 
 def supported(image_shape, conv_layers):
@@ -38,9 +60,10 @@ class Conv1U8Relu(torch.autograd.Function):
         OH, OW = (H - 8) // 4 + 1, (W - 8) // 4 + 1
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
         out = torch.empty((N, 16, OH, OW), dtype=torch.float32, device=obs.device)
+        fn = {"i8": "rl_conv1_u8_forward_i8", "tc": "rl_conv1_u8_forward_tc", "simt": "rl_conv1_u8_forward"}[
+            _impl(FORWARD_IMPL, C, H, W)]
         with torch.cuda.device(obs.device):
-            _lib.call("rl_conv1_u8_forward_tc" if FORWARD_IMPL == "tc" else "rl_conv1_u8_forward", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
-                      N, C, H, W, 1, _lib.stream())
+            _lib.call(fn, _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), N, C, H, W, 1, _lib.stream())
         ctx.obs, ctx.rows = obs, rows
         ctx.save_for_backward(out)
         ctx.mark_non_differentiable()
@@ -53,7 +76,17 @@ class Conv1U8Relu(torch.autograd.Function):
         R, C, H, W = obs.shape
         N = out.shape[0]
         dev = obs.device
-        if WGRAD_IMPL == "tc":
+        impl = _impl(WGRAD_IMPL, C, H, W, N)
+        if impl == "i8":
+            gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
+            gb = torch.empty(16, dtype=torch.float32, device=dev)
+            g = grad_out.contiguous()
+            sc = _scratch(dev, "wgrad_i8", _lib.load().rl_conv1_u8_wgrad_i8_scratch_bytes)
+            with torch.cuda.device(dev):
+                _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(gw),
+                          _lib.ptr(gb), N, C, H, W, _lib.ptr(sc), _lib.stream(), n_launch=3)
+            return gw, gb, None, None
+        if impl == "tc":
             from rlpyt_b200.models.conv2_op import wgrad_scratch
             gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
             gb = torch.empty(16, dtype=torch.float32, device=dev)

@@ -87,6 +87,8 @@ class AlternatingSampler(GpuSampler):
             for s in self.obs_ready_pair[alt]:
                 s.acquire()
             ro.finish()                                      # bootstrap value of this half
+            if self.device.type == "cuda":                   # the DMA out of the step buffer must have run
+                torch.cuda.current_stream(self.device).synchronize()   # before the host zeroes it below
             if np.any(ro.step_np.done):
                 ended = np.where(ro.step_np.done)[0]
                 ro.step_np.action[ended] = 0

@@ -213,6 +213,9 @@ class GpuSampler(BaseSampler):
             s.acquire()
             assert not s.acquire(block=False)  # drained (action_server.py:63)
         ro.finish()
+        # finish() only ENQUEUES the DMA of reward(T-1)/done(T-1) out of the pinned step buffer: the host
+        # must not touch that buffer (the zeroing below) before the copies have been executed.
+        torch.cuda.current_stream(self.device).synchronize()
         if np.any(step_np.done):  # reset at end of batch; ready for the next (action_server.py:67-71)
             ended = np.where(step_np.done)[0]
             step_np.action[ended] = 0

@@ -70,19 +70,51 @@ def gpu_local_cpus(cuda_idx):
     return allowed
 
 
-def make_affinity(cuda_idx, n_workers, local_rank=0, ranks_per_node=1, reserve_master=1):
-    """Affinity dict for the samplers: this rank's share of the GPU-local cores, one core reserved
-    for the master, the rest dealt round-robin to ``n_workers`` workers."""
+def _sibling_groups(cpus):
+    """Group hardware threads into physical cores (``thread_siblings_list`` of sysfs); each group is sorted
+    and the groups are ordered by their first thread.  Falls back to one thread per core."""
+    allowed, groups, seen = set(cpus), [], set()
+    for c in sorted(cpus):
+        if c in seen:
+            continue
+        sib = [c]
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                sib = [x for x in _parse_ranges(f.read().strip()) if x in allowed] or [c]
+        except OSError:
+            pass
+        sib = sorted(set(sib) | {c})
+        seen.update(sib)
+        groups.append(sib)
+    return groups
+
+
+def make_affinity(cuda_idx, n_workers=None, local_rank=0, ranks_per_node=1, node_share=8, smt_workers=False):
+    """Affinity dict for the samplers.  The GPU-local NUMA node's PHYSICAL cores are the unit: ranks whose
+    GPUs share a node split its cores evenly, and a rank never takes more than ``1/node_share`` of the
+    whole machine's cores (an 8-GPU node: one eighth each), so a 1-GPU run uses the host share it would have
+    in an 8-GPU run - weak scaling with fixed per-GPU resources.  The first core of the share belongs to
+    the master; every worker gets its own core (``smt_workers``: its own hardware thread, two per core).
+    Round 1 handed out hardware threads, not cores: at N >= 4 two ranks ended up on the two hyper-threads
+    of the same cores and 14 workers were dealt onto 12 threads (SCALE_r01: sampling 68 -> 109 ms)."""
     local = gpu_local_cpus(cuda_idx)
-    # ranks whose GPUs share a NUMA node split its cores evenly (by local rank order)
+    cores = _sibling_groups(local)
+    all_cores = _sibling_groups(sorted(os.sched_getaffinity(0)))
     share = max(1, min(ranks_per_node, 8))
     same_node = [r for r in range(share) if gpu_local_cpus(r) == local] if share > 1 else [0]
     if len(same_node) > 1 and local_rank in same_node:
         k = same_node.index(local_rank)
-        per = max(1, len(local) // len(same_node))
-        local = local[k * per:(k + 1) * per] or local
-    master = local[:reserve_master]
-    pool = local[reserve_master:] or local
-    n_workers = max(1, n_workers)
-    workers_cpus = [[pool[i % len(pool)]] for i in range(n_workers)]
+        per = max(1, len(cores) // len(same_node))
+        cores = cores[k * per:(k + 1) * per] or cores
+    cap = max(2, len(all_cores) // max(1, node_share)) if node_share else len(cores)
+    cores = cores[:cap]
+    master = list(cores[0])
+    pool = cores[1:] or cores
+    slots = [[c[0]] for c in pool]
+    if smt_workers:
+        slots += [[c[1]] for c in pool if len(c) > 1]
+    if not n_workers:
+        n_workers = len(slots)
+    n_workers = max(1, min(n_workers, len(slots)))
+    workers_cpus = slots[:n_workers]
     return dict(cuda_idx=cuda_idx, master_cpus=master, workers_cpus=workers_cpus, set_affinity=True)

@@ -139,6 +139,91 @@ def test_conv1_wgrad_tcgen05_vs_fp64(shape, n_obs, n_rows):
     assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())
 
 
+@pytest.mark.parametrize("shape", [(4, 84, 84), (4, 36, 36), (4, 104, 80), (4, 8, 8), (4, 64, 128)])
+@pytest.mark.parametrize("n_obs,n_rows,relu", [(257, 130, 1), (3, None, 0), (400, None, 1)])
+def test_conv1_forward_i8_vs_fp64(shape, n_obs, n_rows, relu):
+    """The integer tensor-core first layer (csrc/conv1_i8.cuh: uint8 frames as exact kind::i8 operands, filter
+    bank as four base-128 digits, exact int32 accumulation) against an fp64 convolution: <= 3e-6 of sum|x||w|
+    (the bar of the TF32 kernel; measured ~5e-8), with and without the minibatch row gather, ragged last tiles,
+    weights spanning six orders of magnitude within a channel."""
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    assert _lib.load().rl_conv1_u8_i8_supported(*shape)
+    g = torch.Generator(device="cuda").manual_seed(11 + n_obs)
+    obs = torch.randint(0, 256, (n_obs,) + shape, dtype=torch.uint8, device="cuda", generator=g)
+    rows = torch.randint(0, n_obs, (n_rows,), device="cuda", generator=g) if n_rows else None
+    N = n_rows or n_obs
+    w = (torch.rand(16, 4, 8, 8, device="cuda", generator=g) - 0.5) / 8
+    w.view(-1)[::7] *= 1e-4                                   # low digits
+    w[3] *= 50.0                                              # per-channel scales
+    w[5] = 0.0                                                # an all-zero channel (scale 2^0)
+    b = (torch.rand(16, device="cuda", generator=g) - 0.5) / 8
+    OH, OW = (shape[1] - 8) // 4 + 1, (shape[2] - 8) // 4 + 1
+    y = torch.full((N, 16, OH, OW), float("nan"), device="cuda")
+    _lib.call("rl_conv1_u8_forward_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), N, 4,
+              shape[1], shape[2], relu, _lib.stream())
+    x = (obs if rows is None else obs[rows]).double() / 255
+    ref = F.conv2d(x, w.double(), b.double(), stride=4)
+    ref = F.relu(ref) if relu else ref
+    scale = F.conv2d(x.abs(), w.double().abs(), None, stride=4) + b.double().abs().view(1, 16, 1, 1)
+    assert torch.isfinite(y).all()
+    assert float(((y.double() - ref).abs() / scale.clamp_min(1e-30)).max()) <= 3e-6
+
+
+def test_conv1_i8_rejects_unsupported_geometry():
+    from rlpyt_b200 import _lib
+    lib = _lib.load()
+    assert not lib.rl_conv1_u8_i8_supported(4, 210, 160) and not lib.rl_conv1_u8_i8_supported(4, 84, 82)
+    obs = torch.zeros(2, 4, 84, 82, dtype=torch.uint8, device="cuda")
+    w, b, y = torch.zeros(16, 4, 8, 8, device="cuda"), torch.zeros(16, device="cuda"), torch.zeros(2, 16, 20, 19, device="cuda")
+    with pytest.raises(_lib.B200LibraryError):
+        _lib.call("rl_conv1_u8_forward_i8", _lib.ptr(obs), None, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), 2, 4, 84, 82, 1,
+                  _lib.stream())
+
+
+@pytest.mark.parametrize("shape,n_obs,n_rows,mask", [((4, 84, 84), 70, None, True), ((4, 84, 84), 300, 130, True),
+                                                     ((4, 36, 36), 5, None, False), ((4, 104, 80), 33, 40, True),
+                                                     ((4, 8, 8), 3, None, True), ((4, 64, 128), 9, None, True), ((4, 84, 84), 1000, None, True)])
+def test_conv1_wgrad_i8_vs_fp64(shape, n_obs, n_rows, mask):
+    """Weight/bias gradient of the uint8 first layer on the integer tensor cores (gradient as four base-128 digits
+    against a per-channel power-of-two scale, exact int32 accumulation over every frame of a CTA, fp64 reduction)
+    against an fp64 reference with the same ReLU mask.  Heavy-tailed gradients (a few elements 300x the rest,
+    one channel 1e-4 of the others): 1e-6 of the term-magnitude scale (the TF32 kernel's bar is 1e-5)."""
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(n_obs)
+    obs = torch.randint(0, 256, (n_obs,) + shape, dtype=torch.uint8, device="cuda", generator=g)
+    rows = torch.randint(0, n_obs, (n_rows,), device="cuda", generator=g) if n_rows else None
+    N = n_rows or n_obs
+    OH, OW = (shape[1] - 8) // 4 + 1, (shape[2] - 8) // 4 + 1
+    out = torch.randn(N, 16, OH, OW, device="cuda", generator=g)          # sign = ReLU mask
+    go = torch.randn(N, 16, OH, OW, device="cuda", generator=g) * 1e-3
+    go = torch.where(torch.rand(go.shape, device="cuda", generator=g) < 1 / 64, go * 300, go)
+    go[:, 5] *= 1e-4
+    go[:, 9] = 0.0
+    gw = torch.full((16, 4, 8, 8), float("nan"), device="cuda")
+    gb = torch.full((16,), float("nan"), device="cuda")
+    sc = torch.empty(int(_lib.load().rl_conv1_u8_wgrad_i8_scratch_bytes()) // 4 + 4, device="cuda")
+    _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out) if mask else None, _lib.ptr(go),
+              _lib.ptr(gw), _lib.ptr(gb), N, 4, shape[1], shape[2], _lib.ptr(sc), _lib.stream(), n_launch=3)
+    x = (obs if rows is None else obs[rows]).double() / 255
+    gm = (go * (out > 0)).double() if mask else go.double()
+    w = torch.zeros(16, 4, 8, 8, dtype=torch.float64, device="cuda", requires_grad=True)
+    b = torch.zeros(16, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(x, w, b, stride=4).backward(gm)
+    wa = torch.zeros_like(w, requires_grad=True)
+    F.conv2d(x, wa, None, stride=4).backward(gm.abs())
+    assert torch.isfinite(gw).all() and torch.isfinite(gb).all()
+    assert float(((gw.double() - w.grad).abs() / wa.grad.clamp_min(1e-300)).max()) <= 1e-6
+    assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())
+    assert float(gw[9].abs().max()) == 0.0 and float(gb[9]) == 0.0
+    # deterministic: a second call gives the same bits
+    gw2, gb2 = torch.empty_like(gw), torch.empty_like(gb)
+    _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out) if mask else None, _lib.ptr(go),
+              _lib.ptr(gw2), _lib.ptr(gb2), N, 4, shape[1], shape[2], _lib.ptr(sc), _lib.stream(), n_launch=3)
+    assert torch.equal(gw, gw2) and torch.equal(gb, gb2)
+
+
 @pytest.mark.parametrize("N,plane", [(1, (20, 20)), (64, (20, 20)), (700, (20, 20)), (300, (25, 19)), (2, (7, 5))])
 def test_conv2_wgrad_tcgen05_vs_fp64(N, plane):
     import torch.nn.functional as F

@@ -56,10 +56,36 @@ def test_data_parallel_replicates_rank0_parameters():
 
 def test_affinity_split_is_disjoint_per_rank():
     from rlpyt_b200.utils.affinity import make_affinity
-    a = make_affinity(0, 3, local_rank=0, ranks_per_node=1)
+    a = make_affinity(0, 3, local_rank=0, ranks_per_node=1, node_share=0)       # no per-rank cap: 3 workers fit on 8 cpus
     assert a["set_affinity"] and len(a["workers_cpus"]) == 3 and a["cuda_idx"] == 0
     allowed = set(os.sched_getaffinity(0))
     assert all(set(c) <= allowed for c in a["workers_cpus"]) and set(a["master_cpus"]) <= allowed
+    assert not set(a["master_cpus"]) & {c for w in a["workers_cpus"] for c in w}
+
+
+def test_affinity_physical_cores_two_socket_box(monkeypatch):
+    """The 2-socket B200 host (128 threads: cpu i and i+64 are hyper-threads of one core; GPUs 0-3 on cores 0-31,
+    GPUs 4-7 on cores 32-63): every rank gets 8 whole cores at every N, no hardware thread is handed out twice,
+    and two ranks never share a physical core (round 1 split THREADS and put ranks 0/2 on sibling threads)."""
+    from rlpyt_b200.utils import affinity as A
+    node = {0: list(range(0, 32)) + list(range(64, 96)), 1: list(range(32, 64)) + list(range(96, 128))}
+    monkeypatch.setattr(A, "gpu_local_cpus", lambda idx: node[0 if idx < 4 else 1])
+    monkeypatch.setattr(A, "_sibling_groups",
+                        lambda cpus: [list(t) for t in sorted({tuple(sorted({c % 64, c % 64 + 64} & set(cpus))) for c in cpus})])
+    monkeypatch.setattr(A.os, "sched_getaffinity", lambda pid: set(range(128)))
+    for world in (1, 2, 4, 8):
+        used_threads, used_cores = set(), set()
+        for r in range(world):
+            a = A.make_affinity(r, None, local_rank=r, ranks_per_node=world, node_share=8)
+            threads = set(a["master_cpus"]) | {c for w in a["workers_cpus"] for c in w}
+            cores = {t % 64 for t in threads}
+            assert len(a["workers_cpus"]) == 7 and len(cores) == 8            # 1 master core + 7 worker cores
+            assert not (threads & used_threads) and not (cores & used_cores)
+            assert threads <= set(node[0 if r < 4 else 1])                    # GPU-local socket
+            used_threads |= threads
+            used_cores |= cores
+        a = A.make_affinity(0, None, local_rank=0, ranks_per_node=world, node_share=8, smt_workers=True)
+        assert len(a["workers_cpus"]) == 14 and len({w[0] for w in a["workers_cpus"]}) == 14
 
 
 def test_reference_arm_runs_on_rank0_only():
