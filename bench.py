@@ -131,16 +131,21 @@ def run_b200(args):
     np.random.seed(seed)
     torch.manual_seed(seed)
     SamplerCls = GpuSampler
-    if os.environ.get("RLPYT_B200_BENCH_SAMPLER", "gpu") == "alternating":
+    sampler_kind = os.environ.get("RLPYT_B200_BENCH_SAMPLER", args.sampler)
+    if sampler_kind == "alternating":   # two worker groups: one steps its envs while the GPU serves the other
         from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler as SamplerCls
     sampler = SamplerCls(EnvCls=SyntheticAtariEnv, env_kwargs=ENV_KW, batch_T=T_CFG, batch_B=B_CFG,
                          max_decorrelation_steps=20)
     agent = AtariFfAgent()
     from rlpyt_b200.utils.affinity import make_affinity
     # every GPU gets the same host share at every N: one eighth of the box's PHYSICAL cores (an 8-GPU node),
-    # the first of them for the master, one env worker per remaining core (--smt-workers: per hardware thread)
+    # the first of them for the master, one env worker per hardware thread of the others (--workers-per-core 1:
+    # one per core).  Measured on the 2 x 64-thread host (profiles/r02_sampler_configs.txt): alternating + 14
+    # workers on 7 cores hides the env stepping behind the device half-steps (59 ms per batch; standard 76-79 ms).
     affinity = make_affinity(local_rank, args.workers or None, local_rank=local_rank, ranks_per_node=world,
-                             node_share=8, smt_workers=args.smt_workers)
+                             node_share=8, smt_workers=args.workers_per_core >= 2)
+    if sampler_kind == "alternating" and len(affinity["workers_cpus"]) % 2:
+        affinity["workers_cpus"] = affinity["workers_cpus"][:-1] or affinity["workers_cpus"]
     n_workers = len(affinity["workers_cpus"])
     sampler.initialize(agent, affinity=affinity, seed=seed + 1, bootstrap_value=True, world_size=world, rank=rank)
     agent.to_device(local_rank)
@@ -183,6 +188,9 @@ def run_b200(args):
             itr += 1
         barrier()
         t_sample = 0.0
+        if getattr(sampler, "profile", None):
+            for k in sampler.profile:
+                sampler.profile[k] = 0
         with ClockSampler(local_rank) as clk_e2e:
             t0 = time.perf_counter()
             for _ in range(K):
@@ -196,6 +204,10 @@ def run_b200(args):
             barrier()
             t_e2e = max_over_ranks(time.perf_counter() - t0)
         e2e = steps_per_itr * K / t_e2e
+        sampler_profile = None
+        pr = getattr(sampler, "profile", None)
+        if pr and pr.get("steps"):   # RLPYT_B200_SAMPLER_PROFILE=1: master-side split of one env step
+            sampler_profile = {k[:-2]: pr[k] / pr["steps"] * 1e6 for k in ("wait_envs_s", "device_step_s", "release_s")}
         params_identical = None
         if world > 1:   # data-parallel replicas must hold bit-identical parameters after K+W updates x 16
             flat = algo.optimizer.flat_param if hasattr(algo.optimizer, "flat_param") else torch.cat(
@@ -226,10 +238,11 @@ def run_b200(args):
                                "(BASELINE.json configs[2]; configs[4] at N>1), gamma .99 lambda .98 lr 1e-3 clip .1 4x4",
                    "global_batch": steps_per_itr, "parallelism": f"dp{world}",
                    "l2": "inputs_larger_than_L2 (925 MB observation batch per rank)",
-                   "env_workers_per_rank": n_workers, "host_threads": cores,
+                   "env_workers_per_rank": n_workers, "host_threads": cores, "sampler": sampler_kind,
                    "worker_cpus_rank0": [c[0] for c in affinity["workers_cpus"]], "master_cpus_rank0": affinity["master_cpus"]},
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": t_e2e / K * 1e3, "sampling_ms_per_step_rank0": t_sample / K * 1e3},
+                "ms_per_step": t_e2e / K * 1e3, "sampling_ms_per_step_rank0": t_sample / K * 1e3,
+                "sampler_profile_us_per_env_step_rank0": sampler_profile},
         "gpu_launches": launches,
         "clocks": clk_value.summary(), "clocks_e2e": clk_e2e.summary(),
         "last_opt_info": {k: float(np.mean(getattr(info, k))) for k in info._fields},
@@ -240,13 +253,13 @@ def run_b200(args):
     # ---- roofline of the GAE scan kernel at the HBM-bound size, measured live (rank 0)
     if rank == 0:
         out["roofline"] = roofline_gae(U)
-        try:   # the largest kernel of the timed step, for context next to the metric's own kernel above
-            rk = roofline_conv1_wgrad()
+        try:   # the contraction kernels of the timed step; the largest one is the step's dominant kernel
+            ks = step_kernel_rooflines()
             n_updates = int(PPO_KW.get("epochs", 4)) * int(PPO_KW.get("minibatches", 4))
-            # share of the timed step spent in this kernel (one launch per minibatch update), to compare
-            # with the ncu launch list under profiles/ (serialised, cold-cache: the share must agree)
-            rk["share_of_step"] = rk["us_per_launch"] * n_updates / (out["ms_per_step"] * 1e3)
-            out["roofline_step_kernel"] = rk
+            for k in ks:   # share of the timed step, to compare with the ncu launch list under profiles/
+                k["share_of_step"] = k["us_per_launch"] * k["launches_per_update"] * n_updates / (out["ms_per_step"] * 1e3)
+            out["step_kernels"] = ks
+            out["roofline_step_kernel"] = max(ks, key=lambda k: k["share_of_step"])
         except Exception as e:  # never let the extra measurement break the bench line
             out["roofline_step_kernel"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -293,48 +306,109 @@ def roofline_gae(U, T=128, B=1 << 20, reps=10):
             "peak_source": how, "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes}
 
 
-def roofline_conv1_wgrad(N=8192, reps=10):
-    """The largest kernel of the PPO step (profiles/r01_launches_ppo_iter_v6.csv: ~22 % of the
-    iteration): the tcgen05 weight gradient of the uint8 first layer on one 8192-sample minibatch with
-    the minibatch row gather.  Algorithmic bytes per image: 28 224 B frame + 2 x 25 600 B (output
-    gradient and ReLU mask source), read once; the result is 4 KiB.  CUDA events on the launch stream."""
+def step_kernel_rooflines(N=8192, reps=10):
+    """The contraction kernels of one minibatch update (N = 8192 samples, (4,84,84) frames), each timed alone with
+    CUDA events on the launch stream, with its algorithmic bytes (what has to cross HBM once) against the HBM
+    roof - and, for the fully connected layer, its useful flops against the TF32 tensor roof.  The caller picks
+    the largest one as ``roofline_step_kernel``."""
     from rlpyt_b200 import _lib
     from rlpyt_b200.models.conv2_op import wgrad_scratch
+    from rlpyt_b200.models.gemm_op import gemm_tn
     peak, how = peaks()
+    lib = _lib.load()
     gen = torch.Generator(device="cuda").manual_seed(1)
     obs = torch.randint(0, 256, (4 * N,) + IMAGE, dtype=torch.uint8, device="cuda", generator=gen)   # 925 MB > L2
     rows = torch.randperm(4 * N, device="cuda", generator=gen)[:N].contiguous()
     oh, ow = (IMAGE[1] - 8) // 4 + 1, (IMAGE[2] - 8) // 4 + 1
     o1 = torch.randn(N, 16, oh, ow, device="cuda", generator=gen)
     g1 = torch.randn(N, 16, oh, ow, device="cuda", generator=gen)
-    gw, gb = torch.empty(16, 4, 8, 8, device="cuda"), torch.empty(16, device="cuda")
-    sc = wgrad_scratch(obs.device)
-    fn = lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1),
-                           _lib.ptr(gw), _lib.ptr(gb), N, IMAGE[0], IMAGE[1], IMAGE[2], _lib.ptr(sc), _lib.stream(),
-                           n_launch=2)
+    x2 = torch.relu(o1)
+    oh2, ow2 = (oh - 2) // 2 + 1, (ow - 2) // 2 + 1
+    o2 = torch.randn(N, 32, oh2, ow2, device="cuda", generator=gen)
+    g2 = (torch.randn(N, 32, oh2, ow2, device="cuda", generator=gen) * (o2 > 0)).contiguous()
+    w1, b1 = torch.randn(16, 4, 8, 8, device="cuda", generator=gen) / 16, torch.randn(16, device="cuda", generator=gen)
+    w2, b2 = torch.randn(32, 16, 4, 4, device="cuda", generator=gen) / 16, torch.randn(32, device="cuda", generator=gen)
+    gw1, gb1 = torch.empty_like(w1), torch.empty_like(b1)
+    gw2, gb2 = torch.empty_like(w2), torch.empty_like(b2)
+    gx2 = torch.empty_like(x2)
+    y1, y2 = torch.empty_like(o1), torch.empty_like(o2)
+    sc_i8 = torch.empty(int(lib.rl_conv1_u8_wgrad_i8_scratch_bytes()) // 4 + 4, device="cuda")
+    sc_tc = wgrad_scratch(obs.device)
+    sc_dg = torch.empty(int(lib.rl_conv2_dgrad_tc_scratch_bytes()) // 4 + 4, device="cuda")
+    fa = torch.randn(N, 3200, device="cuda", generator=gen)
+    fb = torch.randn(512, 3200, device="cuda", generator=gen)
+    C, H, W = IMAGE
+    P1, P2 = 16 * oh * ow * 4, 32 * oh2 * ow2 * 4
+    i8 = bool(lib.rl_conv1_u8_i8_supported(C, H, W))
+    kernels = [
+        (("conv1_i8_wgrad_kernel + absmax + reduce (kind::i8)" if i8 else "conv_wgrad_tc_kernel<Layer1>") + " [N=8192, (4,84,84) u8]",
+         (lambda: _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(gw1),
+                            _lib.ptr(gb1), N, C, H, W, _lib.ptr(sc_i8), _lib.stream(), n_launch=3)) if i8 else
+         (lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(gw1),
+                            _lib.ptr(gb1), N, C, H, W, _lib.ptr(sc_tc), _lib.stream(), n_launch=2)),
+         N * (C * H * W + 2 * P1), "conv1_wgrad_bytes_per_launch"),
+        (("conv1_i8_fwd_kernel (kind::i8)" if i8 else "conv_fwd_tc_kernel<Layer1>") + " [N=8192]",
+         lambda: _lib.call("rl_conv1_u8_forward_i8" if i8 else "rl_conv1_u8_forward_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w1),
+                           _lib.ptr(b1), _lib.ptr(y1), N, C, H, W, 1, _lib.stream()),
+         N * (C * H * W + P1), "conv1_fwd_bytes_per_launch"),
+        ("conv_fwd_tc_kernel<Layer2> [N=8192]",
+         lambda: _lib.call("rl_conv2_forward_tc", _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(y2), N, 16, oh, ow, 1, _lib.stream()),
+         N * (P1 + P2), "conv2_fwd_bytes_per_launch"),
+        ("conv_fwd_tc_kernel<Dgrad2> [N=8192]",
+         lambda: _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.ptr(sc_dg), _lib.stream(),
+                           n_launch=2),
+         N * (P1 + P2), "conv2_dgrad_bytes_per_launch"),
+        ("conv_wgrad_tc_kernel<Layer2> [N=8192]",
+         lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x2), None, _lib.ptr(g2), _lib.ptr(gw2), _lib.ptr(gb2), N, 16, oh, ow,
+                           _lib.ptr(sc_tc), _lib.stream(), n_launch=2),
+         N * (P1 + P2), "conv2_wgrad_bytes_per_launch"),
+    ]
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        traffic_tab = {}
+    out = []
+    for name, fn, nbytes, tkey in kernels:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = float(np.mean(ts))
+        out.append({"kernel": name, "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(tkey), "peak_source": how,
+                    "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes, "launches_per_update": 1})
+    # fully connected layer: 3 GEMMs per update (forward, input gradient, weight gradient) of the same size
     for _ in range(3):
-        fn()
+        gemm_tn(fa, fb)
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        gemm_tn(fa, fb)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
     t = float(np.mean(ts))
-    nbytes = N * (IMAGE[0] * IMAGE[1] * IMAGE[2] + 2 * 16 * oh * ow * 4)
-    traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
-            "conv1_wgrad_tc_bytes_per_launch")
+        tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2
+        tsrc = "measured bf16 cuBLAS TF/s / 2 (TF32 runs at half the bf16 rate)"
     except Exception:
-        pass
-    return {"kernel": "conv_wgrad_tc_kernel<Layer1> + wgrad_reduce_kernel [N=8192, (4,84,84) u8]", "bound": "hbm",
-            "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / t / 1e9 / peak,
-            "traffic": traffic, "peak_source": how, "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes,
-            "note": "gather/issue-bound implicit GEMM, far from the HBM roof (DESIGN.md section 3)"}
+        tf32_peak, tsrc = 1125.0, "nominal dense TF32 (B200_PROFILING.md)"
+    fl = 2.0 * N * 512 * 3200
+    out.append({"kernel": "gemm_tf32x3_kernel [8192x512x3200, fp32-accurate 3xTF32]", "bound": "tensor",
+                "achieved": fl / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tf32_peak,
+                "traffic": traffic_tab.get("gemm_fc_bytes_per_launch"), "peak_source": tsrc, "us_per_launch": t * 1e6,
+                "algorithmic_flops": fl, "issued_flops": 3 * fl, "launches_per_update": 3,
+                "note": "useful fp32-equivalent flops; the 3-term split issues 3x as many on the tensor pipe"})
+    return out
 
 
 def cpu_baseline(U):
@@ -564,7 +638,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workers", type=int, default=0, help="env workers per rank (0 = one per physical core of the share)")
-    ap.add_argument("--smt-workers", action="store_true", help="one worker per hardware thread instead of per core")
+    ap.add_argument("--workers-per-core", type=int, default=2, help="env workers per physical core of the rank's share (1 or 2)")
+    ap.add_argument("--sampler", default="alternating", choices=["alternating", "gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-context", action="store_true", help="reference arm: skip the stock-PyTorch-on-GPU context leg")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "gae", "replay", "dqn"])

@@ -255,6 +255,19 @@ int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* o
                          float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
                          void* stream);
 
+/* ------------------------------------------------------------------ second conv layer without im2col expansion
+ * Same contracts as rl_conv2_forward_tc / rl_conv2_dgrad_tc (Conv2d(16->32, k4, s2, p1), fp32 NCHW;
+ * rlpyt/models/conv2d.py:36-44, rlpyt/models/pg/atari_ff_model.py:31-35): space-to-depth "cell" rows, the four 2x2
+ * taps as row-shifted tcgen05 descriptors over one shared-memory tile, images streamed by cp.async.bulk, the input
+ * gradient assembled in shared memory and written by one bulk store; fp32-accurate 3-term TF32.
+ * Requirements: C == 16, OW <= 14, x / gradients 16-byte aligned; rl_conv2_s2d_supported() tells
+ * whether a geometry fits (else use the *_tc entry points).  No scratch. */
+int rl_conv2_s2d_supported(int C, int IH, int IW);
+int rl_conv2_forward_s2d(const float* x, const float* weight, const float* bias, float* out, int64_t N, int C,
+                         int IH, int IW, int relu, void* stream);
+int rl_conv2_dgrad_s2d(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C, int IH,
+                       int IW, void* stream);
+
 /* ------------------------------------------------------------------ DQN loss
  * rlpyt/algos/dqn/dqn.py:230-263 `DQN.loss` after the two network forwards: Q(s,a) selection, (double-)DQN
  * target, y = return_ + (1 - done_n) * disc_n * target_q, Huber loss with threshold delta_clip (delta_clip < 0:

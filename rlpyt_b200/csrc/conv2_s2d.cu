@@ -1,0 +1,51 @@
+// C ABI of the "v2" second-layer kernels (conv2_s2d.cuh): Conv2d(16->32, k4, s2, p1)(+bias)(+ReLU) forward and its
+// input gradient on fp32 NCHW activations (rlpyt/models/conv2d.py:36-44, rlpyt/models/pg/atari_ff_model.py:31-35).
+#include "conv2_s2d.cuh"
+
+using namespace rl::c2s;
+
+extern "C" {
+
+int rl_conv2_s2d_supported(int C, int IH, int IW) {
+    if (!geom_ok(C, IH, IW)) return 0;
+    return dg::smem_ok(make_geom(1, IH, IW)) ? 1 : 0;
+}
+
+int rl_conv2_forward_s2d(const float* x, const float* weight, const float* bias, float* out, int64_t N, int C, int IH,
+                         int IW, int relu, void* stream) {
+    RL_REQUIRE(x && weight && bias && out, RL_EINVAL, "rl_conv2_forward_s2d: null pointer");
+    RL_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && geom_ok(C, IH, IW), RL_EINVAL,
+               "rl_conv2_forward_s2d: needs C=16, OW <= 14 (got C=%d %dx%d)", C, IH, IW);
+    RL_REQUIRE(rl::aligned(x, 16) && rl::aligned(weight, 4), RL_EALIGN, "rl_conv2_forward_s2d: x must be 16-byte aligned");
+    if (N == 0) return RL_OK;
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    const cudaError_t e = launch_fwd(x, weight, bias, out, make_geom(N, IH, IW), relu, sms, rl::as_stream(stream));
+    if (e != cudaSuccess) {
+        rl::set_error("rl_conv2_forward_s2d: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    return RL_OK;
+}
+
+int rl_conv2_dgrad_s2d(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C, int IH, int IW,
+                       void* stream) {
+    RL_REQUIRE(grad_out_masked && weight && grad_x, RL_EINVAL, "rl_conv2_dgrad_s2d: null pointer");
+    RL_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && geom_ok(C, IH, IW), RL_EINVAL,
+               "rl_conv2_dgrad_s2d: needs C=16, OW <= 14 (got C=%d %dx%d)", C, IH, IW);
+    const Geom g = make_geom(N, IH, IW);
+    RL_REQUIRE(dg::smem_ok(g), RL_EINVAL, "rl_conv2_dgrad_s2d: plane too large for the shared-memory stages (%dx%d)", IH, IW);
+    RL_REQUIRE(rl::aligned(grad_out_masked, 16) && rl::aligned(grad_x, 16), RL_EALIGN,
+               "rl_conv2_dgrad_s2d: gradients must be 16-byte aligned (bulk copies)");
+    if (N == 0) return RL_OK;
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    const cudaError_t e = dg::launch_dgrad(grad_out_masked, weight, grad_x, g, sms, rl::as_stream(stream));
+    if (e != cudaSuccess) {
+        rl::set_error("rl_conv2_dgrad_s2d: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    return RL_OK;
+}
+
+}  // extern "C"

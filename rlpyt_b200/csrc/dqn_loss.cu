@@ -40,7 +40,13 @@ dqn_loss_kernel(const float* __restrict__ qs, const float* __restrict__ target_q
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kDqnThreads + threadIdx.x;
     double acc = 0.0;
     if (i < N) {
-        const int a = static_cast<int>(action[i]);
+        // An action outside [0, A) (replay rows of the documented "wrong wrap", a model / env action-space
+        // mismatch) must not become an out-of-bounds access: index 0 is read instead and the sample's Q-value is
+        // poisoned with NaN, so the loss, the TD errors and the gradient of that row are NaN and the caller sees it
+        // (the reference raises an IndexError in select_at_indexes).
+        const int64_t a_raw = action[i];
+        const bool a_bad = a_raw < 0 || a_raw >= A;
+        const int a = a_bad ? 0 : static_cast<int>(a_raw);
         const float* tq = target_qs + i * A;
         float target_q;
         if (next_qs != nullptr) {                       // double DQN: online argmax, target value
@@ -56,7 +62,7 @@ dqn_loss_kernel(const float* __restrict__ qs, const float* __restrict__ target_q
             target_q = tq[0];
             for (int k = 1; k < A; ++k) target_q = fmaxf(target_q, tq[k]);
         }
-        const float q = qs[i * A + a];
+        const float q = a_bad ? __int_as_float(0x7fc00000) : qs[i * A + a];
         const float disc_target_q = __fmul_rn(disc_n, target_q);
         const float not_done = done_n[i] ? 0.0f : 1.0f;
         const float y = __fadd_rn(ret[i], __fmul_rn(not_done, disc_target_q));

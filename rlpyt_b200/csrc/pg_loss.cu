@@ -45,7 +45,12 @@ pg_loss_kernel(const float* __restrict__ prob_new, const float* __restrict__ val
         const float m = (valid != nullptr) ? valid[i] : 1.0f;
         // With no mask the mean's 1/N is known now; with a mask the finalize kernel divides.
         const float w = (valid != nullptr) ? m : 1.0f / static_cast<float>(N);
-        const int a = static_cast<int>(action[i]);
+        // An action outside [0, A) must not become an out-of-bounds access: index 0 is used for the addresses and
+        // the selected probability is poisoned with NaN, so the loss and this row's gradient are NaN and the caller
+        // sees it (the reference raises an IndexError in select_at_indexes, rlpyt/utils/tensor.py:5-15).
+        const int64_t a_raw = action[i];
+        const bool a_bad = a_raw < 0 || a_raw >= A;
+        const int a = a_bad ? 0 : static_cast<int>(a_raw);
         const float* p = prob_new + i * A;
         float ent = 0.0f;
         float pa = 0.0f;
@@ -58,6 +63,7 @@ pg_loss_kernel(const float* __restrict__ prob_new, const float* __restrict__ val
             if (grad_prob != nullptr)                                    // d(-c_ent*ent)/dp_k
                 grad_prob[i * A + k] = (c_ent * w) * (lg + pk / (pk + kEps));
         }
+        if (a_bad) pa = __int_as_float(0x7fc00000);
         const float Ai = adv[i];
         float pi_term, g_pa;  // pi_term enters the mean with sign -1; g_pa = d(pi_loss_i)/dp_a / w
         if (PPO) {

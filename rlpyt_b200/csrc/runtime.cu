@@ -1,5 +1,8 @@
 // Error plumbing + device queries for the C ABI (no kernels here).
+#if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
+#define RL_HAVE_SSE2 1
+#endif
 #include <stdarg.h>
 #include <string.h>
 
@@ -37,9 +40,52 @@ int sm_count() {
 
 }  // namespace rl
 
+#ifdef RL_HAVE_SSE2
+#include <immintrin.h>
+namespace rl {
+// Whole 64-byte lines with non-temporal stores; the widest vector unit the host has (one full line per store on
+// AVX-512 keeps a write-combining buffer busy for a single instruction).  Returns the number of bytes copied.
+__attribute__((target("avx512f"))) static int64_t stream_lines_avx512(uint8_t* d, const uint8_t* s, int64_t n) {
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) _mm512_stream_si512(reinterpret_cast<__m512i*>(d + i), _mm512_loadu_si512(s + i));
+    return i;
+}
+__attribute__((target("avx2"))) static int64_t stream_lines_avx2(uint8_t* d, const uint8_t* s, int64_t n) {
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 32));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 32), b);
+    }
+    return i;
+}
+static int64_t stream_lines_sse2(uint8_t* d, const uint8_t* s, int64_t n) {
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+    }
+    return i;
+}
+static int64_t stream_copy_lines(uint8_t* d, const uint8_t* s, int64_t n) {
+    static const int level = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    const int64_t i = level == 2 ? stream_lines_avx512(d, s, n) : (level == 1 ? stream_lines_avx2(d, s, n) : stream_lines_sse2(d, s, n));
+    _mm_sfence();
+    return i;
+}
+}  // namespace rl
+#endif
+
 extern "C" {
 
-int rl_b200_abi_version(void) { return 1; }
+int rl_b200_abi_version(void) { return 2; }   // 2: + rl_conv1_u8_*_i8
 
 const char* rl_b200_last_error(void) { return rl::g_err; }
 
@@ -62,20 +108,9 @@ int rl_host_stream_copy(void* dst, const void* src, int64_t nbytes) {
     uint8_t* d = static_cast<uint8_t*>(dst);
     const uint8_t* s = static_cast<const uint8_t*>(src);
     int64_t i = 0;
-    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-        const int64_t nv = nbytes / 64;
-        for (int64_t v = 0; v < nv; ++v, i += 64) {
-            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
-            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
-            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
-            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
-            _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
-        }
-        _mm_sfence();
-    }
+#ifdef RL_HAVE_SSE2      // x86 hosts only; on other hosts (Grace/ARM) the whole copy is the memcpy below
+    if ((reinterpret_cast<uintptr_t>(d) & 63) == 0) i = rl::stream_copy_lines(d, s, nbytes);
+#endif
     if (i < nbytes) memcpy(d + i, s + i, static_cast<size_t>(nbytes - i));
     return RL_OK;
 }

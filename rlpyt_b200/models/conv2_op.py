@@ -1,7 +1,8 @@
-"""``Conv2d(16->32, k4, s2, p1) + ReLU`` on the tensor cores (csrc/conv_tc.cu): forward and input
-gradient are tcgen05 implicit GEMMs (the input gradient as four parity-class GEMMs), and so is the
-weight gradient (taps x channels GEMM over all positions; ``RLPYT_B200_CONV_WGRAD=cudnn`` selects
-cuDNN's fp32 kernel for comparison)."""
+"""``Conv2d(16->32, k4, s2, p1) + ReLU`` on the tensor cores.  Forward and input gradient: the "s2d" kernels of
+csrc/conv2_s2d.cuh (space-to-depth cell rows, row-shifted tcgen05 descriptors, bulk-copied images) whenever the
+geometry fits, else the im2col implicit GEMMs of csrc/conv_tc.cu (``RLPYT_B200_CONV2=tc`` forces those).  Weight
+gradient: tcgen05 GEMM over all positions (csrc/conv_tc.cu; ``RLPYT_B200_CONV_WGRAD=cudnn`` selects cuDNN's fp32
+kernel for comparison)."""
 import os
 
 import torch
@@ -11,6 +12,15 @@ from rlpyt_b200.models.gemm_op import relu_backward
 
 _SCRATCH = {}
 WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
+CONV2_IMPL = os.environ.get("RLPYT_B200_CONV2", "s2d")
+_S2D_OK = {}
+
+
+def s2d_supported(C, IH, IW):
+    key = (C, IH, IW)
+    if key not in _S2D_OK:
+        _S2D_OK[key] = bool(_lib.load().rl_conv2_s2d_supported(C, IH, IW))
+    return CONV2_IMPL == "s2d" and _S2D_OK[key]
 
 
 def wgrad_scratch(dev):
@@ -38,8 +48,9 @@ class Conv2ReluTC(torch.autograd.Function):
         OH, OW = (IH - 2) // 2 + 1, (IW - 2) // 2 + 1
         out = torch.empty((N, 32, OH, OW), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.call("rl_conv2_forward_tc", _lib.ptr(x.detach()), _lib.ptr(weight.detach().contiguous()),
-                      _lib.ptr(bias.detach().contiguous()), _lib.ptr(out), N, C, IH, IW, 1, _lib.stream())
+            _lib.call("rl_conv2_forward_s2d" if s2d_supported(C, IH, IW) else "rl_conv2_forward_tc", _lib.ptr(x.detach()),
+                      _lib.ptr(weight.detach().contiguous()), _lib.ptr(bias.detach().contiguous()), _lib.ptr(out),
+                      N, C, IH, IW, 1, _lib.stream())
         ctx.save_for_backward(x, weight, out)
         return out
 
@@ -49,7 +60,12 @@ class Conv2ReluTC(torch.autograd.Function):
         g = relu_backward(grad_out, out)
         gx = gw = gb = None
         N, C, IH, IW = x.shape
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and s2d_supported(C, IH, IW):
+            gx = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx), N, C, IH, IW,
+                          _lib.stream())
+        elif ctx.needs_input_grad[0]:
             dev = x.device
             scratch = _SCRATCH.get(str(dev))
             if scratch is None:

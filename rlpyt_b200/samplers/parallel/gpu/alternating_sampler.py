@@ -61,7 +61,8 @@ class AlternatingSampler(GpuSampler):
         self.rollouts = []
         for sl in self.halves:
             host_h = dict(step_np=host["step_np"][sl], step_pyt=host["step_pyt"][sl],
-                          all_action=host["all_action"][:, sl], all_reward=host["all_reward"][:, sl])
+                          all_action=host["all_action"][:, sl], all_reward=host["all_reward"][:, sl],
+                          pinned=host.get("pinned", False))
             ro = DeviceRollout(self.samples[:, sl], host_h, self.agent, self.device)
             ro.in_action.copy_(host_h["step_pyt"].action)
             self.rollouts.append(ro)
@@ -70,18 +71,30 @@ class AlternatingSampler(GpuSampler):
         """action_server.py:131-173 on the device step engines."""
         T = self.batch_spec.T
         wait_reset = not self.mid_batch_reset
+        import os
+        import time
+        prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
+        clock = time.perf_counter
         for t in range(T):
             for alt in range(2):
                 ro, sl = self.rollouts[alt], self.halves[alt]
+                t0 = clock() if prof is not None else 0.0
                 for s in self.obs_ready_pair[alt]:
                     s.acquire()                              # this half wrote obs(t), reward(t-1), done(t-1)
+                t1 = clock() if prof is not None else 0.0
                 done_now = ro.step_np.done
                 if self.mid_batch_reset and np.any(done_now):
                     for b in np.where(done_now)[0]:
                         self.agent.reset_one(idx=int(b) + sl.start)
                 ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
+                t2 = clock() if prof is not None else 0.0
                 for s in self.act_ready_pair[alt]:
                     s.release()                              # this half steps while the other is served
+                if prof is not None:
+                    prof["wait_envs_s"] += t1 - t0
+                    prof["device_step_s"] += t2 - t1
+                    prof["release_s"] += clock() - t2
+                    prof["steps"] += 0.5                     # two half steps = one env step of the whole batch
         for alt in range(2):
             ro, sl = self.rollouts[alt], self.halves[alt]
             for s in self.obs_ready_pair[alt]:

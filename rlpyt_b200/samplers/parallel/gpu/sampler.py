@@ -16,6 +16,7 @@ iteration, ppo.py:72).
 import ctypes
 import multiprocessing as mp
 import os
+import time
 
 import numpy as np
 import torch
@@ -159,6 +160,7 @@ class GpuSampler(BaseSampler):
                 pass
         self.ctrl.barrier_out.wait()  # workers decorrelated, first observations are in the step buffer
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
+        self.profile = dict(wait_envs_s=0.0, device_step_s=0.0, release_s=0.0, steps=0)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)
         self.samples_pyt = self.samples
         self.eval_collector = build_eval_collector(self, agent, seed)     # after the fork: master-only envs
@@ -199,16 +201,26 @@ class GpuSampler(BaseSampler):
         step_np, ro = self.host["step_np"], self.rollout
         T = self.batch_spec.T
         wait_reset = not self.mid_batch_reset
+        prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
+        clock = time.perf_counter
         for t in range(T):
+            t0 = clock() if prof is not None else 0.0
             for s in obs_ready:
                 s.acquire()  # workers wrote obs(t), reward(t-1), done(t-1)
+            t1 = clock() if prof is not None else 0.0
             done_now = step_np.done
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=b)
             ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
+            t2 = clock() if prof is not None else 0.0
             for s in act_ready:
                 s.release()
+            if prof is not None:   # where a step's wall time goes on the master: waiting for the envs / device / wake-ups
+                prof["wait_envs_s"] += t1 - t0
+                prof["device_step_s"] += t2 - t1
+                prof["release_s"] += clock() - t2
+                prof["steps"] += 1
         for s in obs_ready:
             s.acquire()
             assert not s.acquire(block=False)  # drained (action_server.py:63)

@@ -32,6 +32,7 @@ class DeviceRollout:
         # D2H of the actions): ~30 small launches become one graph launch per env step.  Captured
         # lazily after an eager warm-up batch (cuDNN autotuning cannot run under capture).
         self.use_graphs = os.environ.get("RLPYT_B200_SAMPLER_GRAPHS", "1") == "1"
+        self._warned_unpinned = False
         self._graphs = {}
         self._eager_batches = 0
 
@@ -97,6 +98,15 @@ class DeviceRollout:
     def _run(self, key, body):
         if not (self.use_graphs and self._eager_batches >= 1 and getattr(self.agent, "device", None) is not None
                 and self.agent.device.type == "cuda"):
+            body()
+            return
+        if not self.host.get("pinned", False):
+            # the step body copies out of / into the host step buffer with non_blocking=True: only page-locked
+            # memory may be captured (pin_shared() can fail, e.g. under a locked-memory ulimit) -> stay eager
+            if not self._warned_unpinned:
+                import warnings
+                warnings.warn("rlpyt_b200: the step buffer is not page-locked; sampler steps run eagerly (no CUDA graphs)")
+                self._warned_unpinned = True
             body()
             return
         g = self._graphs.get(key)

@@ -43,6 +43,10 @@ class SpinSemaphore:
 
     def __init__(self, ctx=None, nap_after=2.0):
         import multiprocessing as mp
+        import platform
+        if platform.machine().lower() not in ("x86_64", "amd64"):
+            raise RuntimeError("SpinSemaphore relies on x86-64 total store ordering (plain loads/stores, no fences); "
+                               "use RLPYT_B200_SAMPLER_SYNC=futex on " + platform.machine())
         ctx = ctx or mp
         # two counters on separate cache lines (8 x int64 = 64 B apart)
         self._raw = ctx.RawArray("q", 16)

@@ -80,6 +80,44 @@ def test_conv2_forward_tcgen05_vs_torch(N, plane):
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=2e-5 * s)
 
 
+@pytest.mark.parametrize("impl", ["s2d", "tc"])
+@pytest.mark.parametrize("N,plane", [(1, (20, 20)), (149, (20, 20)), (300, (25, 19)), (7, (8, 6)), (2, (7, 5)), (600, (20, 20))])
+def test_conv2_forward_and_dgrad_vs_fp64(impl, N, plane):
+    """Both implementations of the second layer through the C ABI - "s2d" (csrc/conv2_s2d.cuh: cell rows, row-shifted
+    descriptors, bulk-copied images, input gradient assembled in shared memory) and "tc" (csrc/conv_tc.cu: im2col
+    implicit GEMMs) - against fp64: forward <= 3e-6 of sum|x||w|, input gradient <= 3e-6 of sum|g||w|; every
+    pixel of the input gradient is written (the buffer starts as NaN)."""
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    lib = _lib.load()
+    IH, IW = plane
+    if impl == "s2d" and not lib.rl_conv2_s2d_supported(16, IH, IW):
+        pytest.skip("geometry not supported by the s2d kernels")
+    g = torch.Generator(device="cuda").manual_seed(N + IH)
+    x = torch.relu(torch.randn((N, 16) + plane, device="cuda", generator=g))
+    w = torch.randn(32, 16, 4, 4, device="cuda", generator=g) / 16
+    b = torch.randn(32, device="cuda", generator=g) / 4
+    OH, OW = (IH - 2) // 2 + 1, (IW - 2) // 2 + 1
+    y = torch.full((N, 32, OH, OW), float("nan"), device="cuda")
+    _lib.call("rl_conv2_forward_" + impl, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), N, 16, IH, IW, 1, _lib.stream())
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1))
+    scale = F.conv2d(x.double().abs(), w.double().abs(), None, stride=2, padding=1) + b.double().abs().view(1, 32, 1, 1)
+    assert torch.isfinite(y).all()
+    assert float(((y.double() - ref).abs() / scale).max()) <= 3e-6
+    go = torch.randn(N, 32, OH, OW, device="cuda", generator=g) * (torch.rand(N, 32, OH, OW, device="cuda", generator=g) < 0.7)
+    gx = torch.full((N, 16, IH, IW), float("nan"), device="cuda")
+    if impl == "s2d":
+        _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(go), _lib.ptr(w), _lib.ptr(gx), N, 16, IH, IW, _lib.stream())
+    else:
+        sc = torch.empty(int(lib.rl_conv2_dgrad_tc_scratch_bytes()) // 4 + 4, device="cuda")
+        _lib.call("rl_conv2_dgrad_tc", _lib.ptr(go), _lib.ptr(w), _lib.ptr(gx), N, 16, IH, IW, _lib.ptr(sc), _lib.stream(), n_launch=2)
+    opad = (IH + 2 - 4) - 2 * (OH - 1), (IW + 2 - 4) - 2 * (OW - 1)
+    refx = F.conv_transpose2d(go.double(), w.double(), stride=2, padding=1, output_padding=opad)
+    sx = F.conv_transpose2d(go.double().abs(), w.double().abs(), stride=2, padding=1, output_padding=opad)
+    assert refx.shape == gx.shape and torch.isfinite(gx).all()
+    assert float(((gx.double() - refx).abs() / sx.clamp_min(1e-30)).max()) <= 3e-6
+
+
 @pytest.mark.parametrize("shape", [(4, 84, 84), (4, 36, 36), (4, 104, 80)])
 @pytest.mark.parametrize("use_rows", [False, True])
 def test_conv1_forward_tcgen05_vs_simt(shape, use_rows):

@@ -10,10 +10,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _mk(sampler_cls, T=6, B=8, n_workers=2, image=(4, 36, 36), collector=None, decor=0, p_done=0.1):
+def _mk(sampler_cls, T=6, B=8, n_workers=2, image=(4, 36, 36), collector=None, decor=0, p_done=0.1, p_reward=0.3):
     from rlpyt_b200.agents.pg.atari import AtariFfAgent
     from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
-    kw = dict(EnvCls=SyntheticAtariEnv, env_kwargs=dict(image_shape=image, n_actions=5, p_done=p_done, p_reward=0.3),
+    kw = dict(EnvCls=SyntheticAtariEnv, env_kwargs=dict(image_shape=image, n_actions=5, p_done=p_done, p_reward=p_reward),
               batch_T=T, batch_B=B, max_decorrelation_steps=decor)
     if collector is not None:
         kw["CollectorCls"] = collector
@@ -25,25 +25,34 @@ def _mk(sampler_cls, T=6, B=8, n_workers=2, image=(4, 36, 36), collector=None, d
     return sampler, agent
 
 
-@pytest.mark.parametrize("kind", ["gpu", "serial"])
-def test_sampler_batch_matches_env_replay(kind):
+@pytest.mark.parametrize("kind,image,B,p_done,p_reward", [
+    ("gpu", (4, 36, 36), 8, 0.1, 0.3), ("serial", (4, 36, 36), 8, 0.1, 0.3), ("alternating", (4, 36, 36), 8, 0.1, 0.3),
+    # full-size frames, every step rewarded, half of the steps end an episode: the reward / done of the LAST step of a
+    # batch must be recorded before the master zeroes the step buffer for the next one (round-1 race)
+    ("gpu", (4, 84, 84), 16, 0.5, 1.0), ("alternating", (4, 84, 84), 16, 0.5, 1.0)])
+def test_sampler_batch_matches_env_replay(kind, image, B, p_done, p_reward):
+    """Every sampler fills the [T,B] buffers with exactly what the seeded envs produce under the recorded actions -
+    eager first batch and CUDA-graph replays alike (4 iterations); the alternating sampler (two worker groups,
+    two half-batch step engines) therefore yields the same batch layout as the standard one."""
+    from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler
     from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
     from rlpyt_b200.samplers.serial.sampler import SerialSampler
     from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
-    T, B, image = 6, 8, (4, 36, 36)
-    sampler, agent = _mk(GpuSampler if kind == "gpu" else SerialSampler, T, B, image=image)
+    T = 6
+    cls = dict(gpu=GpuSampler, serial=SerialSampler, alternating=AlternatingSampler)[kind]
+    sampler, agent = _mk(cls, T, B, image=image, p_done=p_done, p_reward=p_reward)
     try:
         # host-side replay: same seeds (worker w gets seed+w, env i of a worker +i; serial: seed+i)
-        if kind == "gpu":
+        if kind != "serial":
             seeds = [11 + w + i for w in range(2) for i in range(B // 2)]
         else:
             seeds = [11 + i for i in range(B)]
-        envs = [SyntheticAtariEnv(image_shape=image, n_actions=5, p_done=0.1, p_reward=0.3) for _ in range(B)]
+        envs = [SyntheticAtariEnv(image_shape=image, n_actions=5, p_done=p_done, p_reward=p_reward) for _ in range(B)]
         obs = []
         for e, s in zip(envs, seeds):
             e.seed(s)
             obs.append(e.reset())
-        for itr in range(2):
+        for itr in range(4):
             samples, traj_infos = sampler.obtain_samples(itr)
             s_obs = samples.env.observation.cpu().numpy()
             s_act = samples.agent.action.cpu().numpy()
