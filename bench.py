@@ -178,6 +178,16 @@ def run_b200(args):
         t_value = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
         launches = _lib.launch_count - l0
         value = steps_per_itr * K / t_value
+        # device time of the returns + loss kernels INSIDE a real optimize_agent iteration (CUDA events around
+        # process_returns and around each fused-loss call; the stream is kept busy by the network kernels, so the
+        # Python/ctypes cost of issuing them is hidden - unlike a stand-alone eager loop)
+        algo.profile_events = []
+        algo.optimize_agent(itr, samples)
+        itr += 1
+        torch.cuda.synchronize()
+        evs = algo.profile_events
+        algo.profile_events = None
+        in_situ_ms = sum(evs[i].elapsed_time(evs[i + 1]) for i in range(0, len(evs) - 1, 2))
 
         # ---- end to end through the public API (host buffers, H2D/D2H inside the timed region)
         for _ in range(W):
@@ -264,6 +274,12 @@ def run_b200(args):
             out["roofline_step_kernel"] = {"error": repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], out["gae_ppo_loss"] = cpu_baseline(U)
+        gl = out["gae_ppo_loss"]
+        gl["gpu_ms_inside_optimize_agent"] = in_situ_ms
+        gl["speedup_inside_optimize_agent"] = gl["cpu_ms"] / in_situ_ms if in_situ_ms > 0 else None
+        gl["note"] = ("gpu_ms_inside_optimize_agent: GAE + 16 fused-loss launches timed with CUDA events inside algo.optimize_agent "
+                      "(the product path); gpu_ms_eager_wall_incl_python: the same kernels issued alone from Python, "
+                      "where the ~25 us per call of ctypes + autograd bookkeeping is exposed")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -340,6 +356,7 @@ def step_kernel_rooflines(N=8192, reps=10):
     C, H, W = IMAGE
     P1, P2 = 16 * oh * ow * 4, 32 * oh2 * ow2 * 4
     i8 = bool(lib.rl_conv1_u8_i8_supported(C, H, W))
+    s2d = bool(lib.rl_conv2_s2d_supported(16, oh, ow))
     kernels = [
         (("conv1_i8_wgrad_kernel + absmax + reduce (kind::i8)" if i8 else "conv_wgrad_tc_kernel<Layer1>") + " [N=8192, (4,84,84) u8]",
          (lambda: _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(gw1),
@@ -351,12 +368,14 @@ def step_kernel_rooflines(N=8192, reps=10):
          lambda: _lib.call("rl_conv1_u8_forward_i8" if i8 else "rl_conv1_u8_forward_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w1),
                            _lib.ptr(b1), _lib.ptr(y1), N, C, H, W, 1, _lib.stream()),
          N * (C * H * W + P1), "conv1_fwd_bytes_per_launch"),
-        ("conv_fwd_tc_kernel<Layer2> [N=8192]",
-         lambda: _lib.call("rl_conv2_forward_tc", _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(y2), N, 16, oh, ow, 1, _lib.stream()),
+        (("conv2_s2d_fwd_kernel" if s2d else "conv_fwd_tc_kernel<Layer2>") + " [N=8192]",
+         lambda: _lib.call("rl_conv2_forward_s2d" if s2d else "rl_conv2_forward_tc", _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(y2),
+                           N, 16, oh, ow, 1, _lib.stream()),
          N * (P1 + P2), "conv2_fwd_bytes_per_launch"),
-        ("conv_fwd_tc_kernel<Dgrad2> [N=8192]",
-         lambda: _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.ptr(sc_dg), _lib.stream(),
-                           n_launch=2),
+        (("conv2_s2d_dgrad_kernel" if s2d else "conv_fwd_tc_kernel<Dgrad2>") + " [N=8192]",
+         (lambda: _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.stream())) if s2d else
+         (lambda: _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.ptr(sc_dg), _lib.stream(),
+                            n_launch=2)),
          N * (P1 + P2), "conv2_dgrad_bytes_per_launch"),
         ("conv_wgrad_tc_kernel<Layer2> [N=8192]",
          lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x2), None, _lib.ptr(g2), _lib.ptr(gw2), _lib.ptr(gb2), N, 16, oh, ow,

@@ -267,6 +267,30 @@ int rl_conv2_forward_s2d(const float* x, const float* weight, const float* bias,
                          int IH, int IW, int relu, void* stream);
 int rl_conv2_dgrad_s2d(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C, int IH,
                        int IW, void* stream);
+/* Weight / bias gradient in the same cell space (grad_out already ReLU-masked): both operands MN-major with
+ * K = cells, M = 64 accumulators per tap promoted to fp32 registers per image, per-CTA partials reduced in a
+ * fixed order.  grad_weight [32,16,4,4], grad_bias [32] (nullable); scratch: rl_conv2_wgrad_s2d_scratch_bytes(). */
+int64_t rl_conv2_wgrad_s2d_scratch_bytes(void);
+int rl_conv2_wgrad_s2d(const float* x, const float* grad_out_masked, float* grad_weight, float* grad_bias, int64_t N,
+                       int C, int IH, int IW, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ Categorical.sample (agent.step)
+ * rlpyt/distributions/categorical.py:25-30 (torch.multinomial over the trailing dim) as an inverse-CDF draw:
+ * action[i] = #{k < A-1 : u_i >= cumsum_fp32(prob[i])[k]} (oracle/pg_loss.py:sample_categorical).  prob [N,A] f32.
+ * uniform [N] f32 in [0,1): injected draws (bit-exact parity with the oracle) - or NULL, then u_i is the first
+ * Philox4x32-10 word of counter (i, rng_state[1]) under key rng_state[0], top 24 bits; rng_state is int64[2] =
+ * {seed, call counter} in DEVICE memory and the kernel increments the counter, so a captured launch draws new
+ * numbers at every graph replay.  uniform_out [N] (nullable) receives the uniforms used.  One 256-thread block. */
+int rl_categorical_sample_f32(const float* prob, const float* uniform, int64_t* rng_state, int64_t* action,
+                              float* uniform_out, int64_t N, int A, void* stream);
+/* The policy head of agent.step in one launch (rlpyt/models/pg/atari_ff_model.py:56-58, rlpyt/agents/pg/
+ * categorical.py:37-39): prob = softmax(h w_pi^T + b_pi) [B,A], value = h w_v + b_v [B], action ~ prob (rule and
+ * Philox stream of rl_categorical_sample_f32; row i uses counter (i, rng_state[1])).  h [B,F], w_pi [A,F], b_pi [A],
+ * w_v [F], b_v [1] f32, A <= 32.  rng_state: int64[3] in device memory = {seed, call counter, 0 (block ticket)} -
+ * the last block increments the counter - or NULL with injected `uniform` [B]. */
+int rl_pg_head_sample_f32(const float* h, const float* w_pi, const float* b_pi, const float* w_v, const float* b_v,
+                          const float* uniform, int64_t* rng_state, float* prob, float* value, int64_t* action,
+                          int64_t B, int F, int A, void* stream);
 
 /* ------------------------------------------------------------------ DQN loss
  * rlpyt/algos/dqn/dqn.py:230-263 `DQN.loss` after the two network forwards: Q(s,a) selection, (double-)DQN

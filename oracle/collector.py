@@ -15,8 +15,12 @@ from oracle import atari_ff
 
 class SerialRollout:
 
-    def __init__(self, envs, state_dict, T, n_actions):
+    def __init__(self, envs, state_dict, T, n_actions, agent_fn=None):
+        """``agent_fn(obs, prev_action, prev_reward) -> (action, prob, value)`` (torch-CPU tensors) replaces the
+        network + multinomial draw - used to pin this loop to the reference's SerialSampler under a deterministic
+        policy (tests/golden/collector.npz, tests/test_oracle_collector.py)."""
         self.envs, self.sd, self.T, self.A = envs, state_dict, T, n_actions
+        self.agent_fn = agent_fn
         B = len(envs)
         obs0 = np.stack([e.reset() for e in envs])
         self.observation = obs0.copy()
@@ -40,8 +44,13 @@ class SerialRollout:
         buf["all_reward"][0] = self.prev_reward
         for t in range(T):
             buf["observation"][t] = self.observation                              # :37
-            pi, v = atari_ff.forward(sd, torch.from_numpy(self.observation))       # categorical.py:37
-            action = torch.multinomial(pi, num_samples=1).squeeze(-1).numpy()      # categorical.py:29
+            if self.agent_fn is not None:
+                a_t, pi, v = self.agent_fn(torch.from_numpy(self.observation), torch.from_numpy(self.prev_action),
+                                           torch.from_numpy(self.prev_reward))
+                action = a_t.numpy()
+            else:
+                pi, v = atari_ff.forward(sd, torch.from_numpy(self.observation))       # categorical.py:37
+                action = torch.multinomial(pi, num_samples=1).squeeze(-1).numpy()      # categorical.py:29
             for b, env in enumerate(self.envs):                                    # :41-54
                 o, r, d, info = env.step(action[b])
                 if getattr(info, "traj_done", d):
@@ -54,6 +63,10 @@ class SerialRollout:
             buf["prob"][t] = pi.numpy()
             buf["value"][t] = v.numpy()
             self.prev_action = action
-        _, v = atari_ff.forward(sd, torch.from_numpy(self.observation))            # :61-63
+        if self.agent_fn is not None:
+            _, _, v = self.agent_fn(torch.from_numpy(self.observation), torch.from_numpy(self.prev_action),
+                                    torch.from_numpy(self.prev_reward))
+        else:
+            _, v = atari_ff.forward(sd, torch.from_numpy(self.observation))            # :61-63
         buf["bootstrap_value"][0] = v.numpy()
         return buf

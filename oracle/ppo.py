@@ -37,9 +37,11 @@ class PpoOracle:
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.p.items()}
 
-    def optimize_agent(self, itr, obs, action, reward, done, value, old_prob, bootstrap_value):
+    def optimize_agent(self, itr, obs, action, reward, done, value, old_prob, bootstrap_value, max_updates=None):
         """obs [T,B,C,H,W] u8, action [T,B] i64, reward/value [T,B] f32, done [T,B] bool,
-        old_prob [T,B,A], bootstrap_value [1,B].  Returns dict of per-update lists (OptInfo)."""
+        old_prob [T,B,A], bootstrap_value [1,B].  Returns dict of per-update lists (OptInfo).
+        ``max_updates`` (tests only): stop after that many minibatch updates - the full-size parity test checks the
+        first update of a [128,256] iteration without paying for the other fifteen on the CPU."""
         T, B = reward.shape
         ret, adv, valid = returns.process_returns(
             np.asarray(reward), np.asarray(done), np.asarray(value), np.asarray(bootstrap_value),
@@ -57,6 +59,8 @@ class PpoOracle:
             indexes = np.arange(batch_size)
             np.random.shuffle(indexes)                                               # misc.py:10-12
             for start in range(0, batch_size - mb_size + 1, mb_size):
+                if max_updates is not None and len(info["loss"]) >= max_updates:
+                    return info
                 idxs = indexes[start:start + mb_size]
                 Ti, Bi = idxs % T, idxs // T                                         # ppo.py:94-95
                 self.opt.zero_grad()

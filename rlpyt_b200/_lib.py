@@ -64,6 +64,10 @@ SIGNATURES = {
     "rl_conv2_s2d_supported": (c_int, [c_int, c_int, c_int]),
     "rl_conv2_forward_s2d": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "rl_conv2_dgrad_s2d": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rl_categorical_sample_f32": (c_int, [P, P, P, P, P, c_int64, c_int, P]),
+    "rl_conv2_wgrad_s2d_scratch_bytes": (c_int64, []),
+    "rl_conv2_wgrad_s2d": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
+    "rl_pg_head_sample_f32": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, P]),
     "rl_a2c_loss_f32": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_float, c_float, P, P, P, P, P]),
 }
 

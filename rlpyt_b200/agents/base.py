@@ -1,5 +1,5 @@
 """Agent base class: glue between sampler, network and algorithm (host-side mirror of
-``rlpyt/agents/base.py:17-246``; synchronous path only - the async/alternating machinery of the
+``rlpyt/agents/base.py:17-246`` plus the recurrent-state mixins of :252-371; the async machinery of the
 reference is out of scope).
 
 B200 design differences, all behind the unchanged method names:
@@ -117,3 +117,109 @@ class BaseAgent:
 
     def toggle_alt(self):
         pass
+
+
+class RecurrentAgentMixin:
+    """Keeps the recurrent state between ``step`` calls so the sampler stays agnostic (mirror of
+    ``rlpyt/agents/base.py:252-306``; use as ``class MyAgent(RecurrentAgentMixin, MyAgentBase)``).  The state is a
+    namedarraytuple of ``[N,B,H]`` tensors (cuDNN layout) that lives on the agent's device; ``None`` means zeros."""
+
+    recurrent = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._prev_rnn_state = None
+        self._sample_rnn_state = None      # parked while training / evaluating
+
+    def reset(self):
+        self._prev_rnn_state = None
+
+    def reset_one(self, idx):
+        if self._prev_rnn_state is not None:
+            self._prev_rnn_state[:, idx] = 0      # every leaf, column idx
+
+    def advance_rnn_state(self, new_rnn_state):
+        """Called by the agent at the end of ``step``."""
+        self._prev_rnn_state = new_rnn_state
+
+    @property
+    def prev_rnn_state(self):
+        return self._prev_rnn_state
+
+    def train_mode(self, itr):
+        if self._mode == "sample":
+            self._sample_rnn_state = self._prev_rnn_state
+        self._prev_rnn_state = None
+        super().train_mode(itr)
+
+    def sample_mode(self, itr):
+        if self._mode != "sample":
+            self._prev_rnn_state = self._sample_rnn_state
+        super().sample_mode(itr)
+
+    def eval_mode(self, itr):
+        if self._mode == "sample":
+            self._sample_rnn_state = self._prev_rnn_state
+        self._prev_rnn_state = None
+        super().eval_mode(itr)
+
+
+class AlternatingRecurrentAgentMixin:
+    """Two recurrent states, swapped by ``advance_rnn_state`` - for the alternating samplers, where two groups of
+    environments take turns stepping (mirror of ``rlpyt/agents/base.py:309-371``)."""
+
+    recurrent = True
+    alternating = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._alt = 0
+        self._prev_rnn_state = None
+        self._prev_rnn_state_pair = [None, None]
+        self._sample_rnn_state_pair = [None, None]
+
+    def reset(self):
+        self._prev_rnn_state_pair = [None, None]
+        self._prev_rnn_state = None
+        self._alt = 0
+
+    # NOTE: like the reference's mixin (agents/base.py:309-371) this one has no ``reset_one``: an alternating
+    # recurrent agent keeps its state across episode ends inside a batch (BaseAgent.reset_one is a no-op).
+
+    def advance_rnn_state(self, new_rnn_state):
+        self._prev_rnn_state_pair[self._alt] = new_rnn_state
+        self._alt ^= 1
+        self._prev_rnn_state = self._prev_rnn_state_pair[self._alt]
+
+    @property
+    def prev_rnn_state(self):
+        return self._prev_rnn_state
+
+    def _park(self):
+        if self._mode == "sample":
+            self._sample_rnn_state_pair = self._prev_rnn_state_pair
+        self._prev_rnn_state_pair = [None, None]
+        self._prev_rnn_state = None
+        self._alt = 0
+
+    def train_mode(self, itr):
+        self._park()
+        super().train_mode(itr)
+
+    def eval_mode(self, itr):
+        self._park()
+        super().eval_mode(itr)
+
+    def sample_mode(self, itr):
+        if self._mode != "sample":
+            self._prev_rnn_state_pair = self._sample_rnn_state_pair
+            self._alt = 0
+            self._prev_rnn_state = self._prev_rnn_state_pair[0]
+        super().sample_mode(itr)
+
+    def get_alt(self):
+        return self._alt
+
+    def toggle_alt(self):
+        self._alt ^= 1
+        self._prev_rnn_state = self._prev_rnn_state_pair[self._alt]

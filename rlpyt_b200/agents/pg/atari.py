@@ -1,6 +1,8 @@
-"""Atari policy-gradient agents (mirror of ``rlpyt/agents/pg/atari.py:9-25``)."""
-from rlpyt_b200.agents.pg.categorical import CategoricalPgAgent
+"""Atari policy-gradient agents (mirror of ``rlpyt/agents/pg/atari.py:9-37``)."""
+from rlpyt_b200.agents.pg.categorical import (AlternatingRecurrentCategoricalPgAgent, CategoricalPgAgent,
+                                              RecurrentCategoricalPgAgent)
 from rlpyt_b200.models.pg.atari_ff_model import AtariFfModel
+from rlpyt_b200.models.pg.atari_lstm_model import AtariLstmModel
 
 
 class AtariMixin:
@@ -13,4 +15,16 @@ class AtariMixin:
 class AtariFfAgent(AtariMixin, CategoricalPgAgent):
 
     def __init__(self, ModelCls=AtariFfModel, **kwargs):
+        super().__init__(ModelCls=ModelCls, **kwargs)
+
+
+class AtariLstmAgent(AtariMixin, RecurrentCategoricalPgAgent):
+
+    def __init__(self, ModelCls=AtariLstmModel, **kwargs):
+        super().__init__(ModelCls=ModelCls, **kwargs)
+
+
+class AlternatingAtariLstmAgent(AtariMixin, AlternatingRecurrentCategoricalPgAgent):
+
+    def __init__(self, ModelCls=AtariLstmModel, **kwargs):
         super().__init__(ModelCls=ModelCls, **kwargs)

@@ -47,14 +47,18 @@ class A2C(PolicyGradientAlgo):
 
     def loss(self, samples):
         """a2c.py:63-103; everything on the device."""
-        if self.agent.recurrent:
-            raise NotImplementedError("recurrent A2C is outside the accelerated path (SURVEY.md 8f)")
         agent_inputs = AgentInputs(
             observation=self._on_device(samples.env.observation),
             prev_action=self._on_device(samples.agent.prev_action),
             prev_reward=self._on_device(samples.env.prev_reward),
         )
-        dist_info, value = self.agent(*agent_inputs)
+        if self.agent.recurrent:                                          # a2c.py:73-79
+            from rlpyt_b200.utils.buffer import buffer_method, buffer_to
+            init = buffer_to(samples.agent.agent_info.prev_rnn_state[0], device=self._device())       # T = 0: [B,N,H]
+            init = buffer_method(buffer_method(init, "transpose", 0, 1), "contiguous")
+            dist_info, value, _rnn_state = self.agent(*agent_inputs, init)
+        else:
+            dist_info, value = self.agent(*agent_inputs)
         return_, advantage, valid = self.process_returns(samples)
         action = self._on_device(samples.agent.action)
         loss, sc = loss_ops.a2c_loss(dist_info.prob, value, action, return_, advantage, valid,

@@ -9,6 +9,7 @@ Where the time went in the reference and what replaces it:
 * loss arithmetic on CPU with D2H of the network outputs -> one fused forward+gradient kernel;
 * DDP all-reduce + clip_grad_norm_ + Adam -> ``FlatAdam.clip_and_step`` (1 NCCL call, 2 kernels);
 * 4 ``.item()`` host syncs per update (:106-109) -> one D2H of all OptInfo rows per iteration.
+Recurrent agents (ppo.py:84-100, 127-131) train on whole trajectories, minibatches over B: ``_optimize_recurrent``.
 """
 import numpy as np
 import torch
@@ -17,6 +18,7 @@ from rlpyt_b200.agents.base import AgentInputs
 from rlpyt_b200.algos.optim import FlatAdam
 from rlpyt_b200.algos.pg import loss_ops
 from rlpyt_b200.algos.pg.base import PolicyGradientAlgo, OptInfo
+from rlpyt_b200.utils.buffer import buffer_method, buffer_to
 from rlpyt_b200.utils.collections import namedarraytuple
 from rlpyt_b200.utils.gather import gather_rows, gather_rows_multi, LazyRows
 from rlpyt_b200.utils.misc import iterate_mb_idxs
@@ -56,16 +58,21 @@ class PPO(PolicyGradientAlgo):
             self._ratio_clip = self.ratio_clip
 
     def optimize_agent(self, itr, samples):
-        """ppo.py:59-115 (feed-forward agents; the recurrent branch is out of scope)."""
+        """ppo.py:59-115.  Feed-forward agents: shuffled [T*B] minibatches through the fused row gathers below;
+        recurrent agents: whole trajectories, minibatches over B only (``_optimize_recurrent``)."""
         if self.agent.recurrent:
-            raise NotImplementedError("recurrent PPO is outside the accelerated path (SURVEY.md section 8f)")
+            return self._optimize_recurrent(itr, samples)
         dev = self._device()
         obs = self._on_device(samples.env.observation)               # ppo.py:67-72 (no-op when resident)
         prev_action = self._on_device(samples.agent.prev_action)
         prev_reward = self._on_device(samples.env.prev_reward)
         if hasattr(self.agent, "update_obs_rms"):
             self.agent.update_obs_rms(obs)
+        prof = getattr(self, "profile_events", None)   # bench.py: device time of the returns + loss kernels inside a real iteration
+        ev = (lambda: None) if prof is None else (lambda: prof.append(_recorded_event()))
+        ev()
         return_, advantage, valid = self.process_returns(samples)     # ppo.py:75
+        ev()
         action = self._on_device(samples.agent.action)
         old_prob = self._on_device(samples.agent.agent_info.dist_info.prob)
         T, B = samples.env.reward.shape[:2]
@@ -92,8 +99,10 @@ class PPO(PolicyGradientAlgo):
                 pa_mb, pr_mb, act_mb, ret_mb, adv_mb, oldp_mb = got[:6]
                 valid_mb = got[6] if valid is not None else None
                 dist_info, value = self.agent(obs_mb, pa_mb, pr_mb)    # ppo.py:133
+                ev()
                 loss, sc = loss_ops.ppo_loss(dist_info.prob, value, oldp_mb, act_mb, ret_mb, adv_mb, valid_mb,
                                              self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
+                ev()
                 loss.backward()                                        # ppo.py:101
                 if fused_opt:
                     grad_norm = self.optimizer.clip_and_step(self.clip_grad_norm)
@@ -112,11 +121,68 @@ class PPO(PolicyGradientAlgo):
         return OptInfo(loss=host[:, 0].tolist(), gradNorm=host[:, 1].tolist(),
                        entropy=host[:, 2].tolist(), perplexity=host[:, 3].tolist())
 
+    def _optimize_recurrent(self, itr, samples):
+        """The recurrent branch of ppo.py:59-115 (:84-86 ``init_rnn_state = prev_rnn_state[0]`` kept ``[B,N,H]`` for
+        slicing, :89-97 minibatches of whole trajectories over B with ``T_idxs = slice(None)``, :127-131 transpose to
+        ``[N,B,H]`` for cuDNN).  ``valid`` masks the steps after an episode end inside the batch (pg/base.py:60-63);
+        the loss arithmetic is the same fused kernel, over [T*mb] rows."""
+        dev = self._device()
+        obs = self._on_device(samples.env.observation)
+        prev_action = self._on_device(samples.agent.prev_action)
+        prev_reward = self._on_device(samples.env.prev_reward)
+        return_, advantage, valid = self.process_returns(samples)
+        action = self._on_device(samples.agent.action)
+        old_prob = self._on_device(samples.agent.agent_info.dist_info.prob)
+        init_rnn_state = buffer_to(samples.agent.agent_info.prev_rnn_state[0], device=dev)     # T = 0: [B,N,H]
+        T, B = samples.env.reward.shape[:2]
+        mb_size = B // self.minibatches
+        n_updates = self.epochs * (B // mb_size)
+        stats = torch.zeros((n_updates, 4), dtype=torch.float32, device=dev)
+        fused_opt = isinstance(self.optimizer, FlatAdam)
+        u = 0
+        for _ in range(self.epochs):
+            for idxs in iterate_mb_idxs(B, mb_size, shuffle=True):
+                cols = torch.from_numpy(np.ascontiguousarray(idxs)).to(dev, non_blocking=True)
+                sel = lambda x: x.index_select(1, cols)
+                self.optimizer.zero_grad()
+                rnn_state = buffer_method(buffer_method(init_rnn_state[cols], "transpose", 0, 1), "contiguous")
+                dist_info, value, _next = self.agent(sel(obs).contiguous(), sel(prev_action), sel(prev_reward), rnn_state)
+                loss, sc = loss_ops.ppo_loss(dist_info.prob, value, sel(old_prob), sel(action), sel(return_), sel(advantage),
+                                             None if valid is None else sel(valid), self.ratio_clip,
+                                             self.value_loss_coeff, self.entropy_loss_coeff)
+                loss.backward()
+                if fused_opt:
+                    grad_norm = self.optimizer.clip_and_step(self.clip_grad_norm)
+                else:
+                    grad_norm = torch.nn.utils.clip_grad_norm_(self.agent.parameters(), self.clip_grad_norm)
+                    self.optimizer.step()
+                stats[u, 0] = sc[0]
+                stats[u, 1] = grad_norm.reshape(())
+                stats[u, 2:4] = sc[1:3]
+                u += 1
+                self.update_counter += 1
+        if self.linear_lr_schedule:
+            self.lr_scheduler.step()
+            self.ratio_clip = self._ratio_clip * (self.n_itr - itr) / self.n_itr
+        host = stats[:u].cpu().numpy().astype(np.float64)
+        return OptInfo(loss=host[:, 0].tolist(), gradNorm=host[:, 1].tolist(),
+                       entropy=host[:, 2].tolist(), perplexity=host[:, 3].tolist())
+
     def loss(self, agent_inputs, action, return_, advantage, valid, old_dist_info, init_rnn_state=None):
         """ppo.py:117-154 signature; returns device 0-dim tensors ``(loss, entropy, perplexity)``."""
-        if init_rnn_state is not None:
-            raise NotImplementedError("recurrent PPO is outside the accelerated path")
+        if init_rnn_state is not None:                                    # [B,N,H] -> [N,B,H] (ppo.py:127-131)
+            init_rnn_state = buffer_method(buffer_method(init_rnn_state, "transpose", 0, 1), "contiguous")
+            dist_info, value, _rnn = self.agent(*agent_inputs, init_rnn_state)
+            loss, sc = loss_ops.ppo_loss(dist_info.prob, value, old_dist_info.prob, action, return_, advantage,
+                                         valid, self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
+            return loss, sc[1], sc[2]
         dist_info, value = self.agent(*agent_inputs)
         loss, sc = loss_ops.ppo_loss(dist_info.prob, value, old_dist_info.prob, action, return_, advantage,
                                      valid, self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
         return loss, sc[1], sc[2]
+
+
+def _recorded_event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e

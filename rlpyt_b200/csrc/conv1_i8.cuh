@@ -644,29 +644,39 @@ conv1_i8_wgrad_kernel(const uint8_t* __restrict__ X, const int64_t* __restrict__
 }
 
 // dW[oc][c][ky][kx] = S_oc / (64 * 255) * sum_cta sum_d 128^-d * partial[cta][by][m][d*16 + oc]  (fp64, fixed order),
-// db[oc] = sum_cta partial_bias[cta][oc].  Thread = (by, m, oc) with oc fastest: 64-byte coalesced reads.
+// db[oc] = sum_cta partial_bias[cta][oc].  One block per (by, m) row of 64 ints: thread = (CTA slice p of 8, oc);
+// every thread sums its CTAs (p, p+8, ...) in order, the 8 slices are added in order through shared memory.
 __global__ void __launch_bounds__(128)
 wgrad_i8_reduce_kernel(const int* __restrict__ partial, const float* __restrict__ partial_bias, const float* __restrict__ gmax,
                        int n_cta, float* __restrict__ dW, float* __restrict__ db) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;     // 2 * 128 * 16 = 4096 outputs
-    if (tid >= 2 * kRows * kOC) return;
-    const int oc = tid & 15, m = (tid >> 4) & 127, by = tid >> 11;
-    double acc = 0.0;
-    for (int cta = 0; cta < n_cta; ++cta) {
-        const int* p = partial + ((static_cast<int64_t>(cta) * 2 + by) * kRows + m) * kN + oc;
-        acc += static_cast<double>(p[0]) + static_cast<double>(p[16]) * (1.0 / 128.0) + static_cast<double>(p[32]) * (1.0 / 16384.0) +
-               static_cast<double>(p[48]) * (1.0 / 2097152.0);
-    }
-    int e = 0;
-    const float gm = gmax[oc];
-    if (gm > 0.0f) frexpf(gm, &e);
-    const double scale = ldexp(1.0, e) / (64.0 * 255.0);
-    const int bx = m >> 6, c = (m >> 4) & 3, kyp = (m >> 2) & 3, kxp = m & 3;
-    dW[((oc * 4 + c) * 8 + 4 * by + kyp) * 8 + 4 * bx + kxp] = static_cast<float>(acc * scale);
-    if (db != nullptr && tid < kOC) {
-        double b = 0.0;
-        for (int cta = 0; cta < n_cta; ++cta) b += static_cast<double>(partial_bias[cta * kOC + tid]);
-        db[tid] = static_cast<float>(b);
+    __shared__ double part[8][kOC];
+    const int row = blockIdx.x;                                  // by * 128 + m
+    const int oc = threadIdx.x & 15, p = threadIdx.x >> 4;
+    if (row < 2 * kRows) {
+        double acc = 0.0;
+        for (int cta = p; cta < n_cta; cta += 8) {
+            const int* q = partial + (static_cast<int64_t>(cta) * 2 * kRows + row) * kN + oc;
+            acc += static_cast<double>(q[0]) + static_cast<double>(q[16]) * (1.0 / 128.0) + static_cast<double>(q[32]) * (1.0 / 16384.0) +
+                   static_cast<double>(q[48]) * (1.0 / 2097152.0);
+        }
+        part[p][oc] = acc;
+        __syncthreads();
+        if (p == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += part[k][oc];
+            int e = 0;
+            const float gm = gmax[oc];
+            if (gm > 0.0f) frexpf(gm, &e);
+            const double scale = ldexp(1.0, e) / (64.0 * 255.0);
+            const int by = row >> 7, m = row & 127;
+            const int bx = m >> 6, c = (m >> 4) & 3, kyp = (m >> 2) & 3, kxp = m & 3;
+            dW[((oc * 4 + c) * 8 + 4 * by + kyp) * 8 + 4 * bx + kxp] = static_cast<float>(t * scale);
+        }
+    } else if (db != nullptr && threadIdx.x < kOC) {             // the extra block: bias
+        double bsum = 0.0;
+        for (int cta = 0; cta < n_cta; ++cta) bsum += static_cast<double>(partial_bias[cta * kOC + threadIdx.x]);
+        db[threadIdx.x] = static_cast<float>(bsum);
     }
 }
 
@@ -696,7 +706,7 @@ inline cudaError_t launch_wgrad(const uint8_t* X, const int64_t* rows, const flo
     if (e != cudaSuccess) return e;
     absmax_kernel<<<sms * 8, 256, 0, st>>>(G, static_cast<int64_t>(g.n_img) * kOC, P, reinterpret_cast<unsigned int*>(gmax));
     conv1_i8_wgrad_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(X, rows, Out, G, gmax, partial, partial_bias, g);
-    wgrad_i8_reduce_kernel<<<(2 * kRows * kOC + 127) / 128, 128, 0, st>>>(partial, partial_bias, gmax, grid, dW, db);
+    wgrad_i8_reduce_kernel<<<2 * kRows + 1, 128, 0, st>>>(partial, partial_bias, gmax, grid, dW, db);
     return cudaGetLastError();
 }
 

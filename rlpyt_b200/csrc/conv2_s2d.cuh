@@ -538,5 +538,298 @@ inline cudaError_t launch_dgrad(const float* G, const float* W, float* dX, const
 
 }  // namespace dg
 
+
+// ====================================================================================================
+// Weight + bias gradient of the same layer in cell space:
+//     dW[oc, c, 2by+dy, 2bx+dx] = sum_{n, cells r} g[n][r][oc] * cell_n[r + by*GW + bx][(c,dy,dx)]
+// (g = the ReLU-masked output gradient on the cell grid, zero for the dropped cells).  Both operands are read
+// MN-major with K = cells: A = the cell rows [r][64 floats] the forward kernel stages (two 128-byte planes = the
+// two 32-element M atoms of an M = 64 operand, LBO = the plane stride), shifted in the K direction per tap;
+// B = the gradient rows [r][32 oc] the input-gradient kernel stages.  D_tap = [64 x 32] per tap in TMEM (an M = 64
+// accumulator lives in lanes 0-15 / 32-47 / 64-79 / 96-111, tcgen05_shift_probe).  The tensor-core accumulator
+// truncates, so every image's partial (K = 128 cells) is promoted into fp32 registers by eight accumulator warps
+// (two TMEM buffers: the drain of image i overlaps the MMAs of image i+1); per-CTA partial sums are reduced over
+// CTAs in a fixed order (deterministic).  3-term TF32 split, 192 MMAs (M=64, N=32, K=8) per image.
+namespace wg2 {
+
+constexpr int kThreadsW = 576;                 // warps 0-7 re-layout, 8-15 accumulators, 16 MMA + TMEM, 17 loader
+constexpr int kAccWarp0 = 8, kMmaWarpW = 16, kLoadWarpW = 17;
+constexpr int kGPlane = kSlotRows * 128;       // gradient rows [144][32 oc], one term
+constexpr int kTmemColsW = 256;                // 2 buffers x 4 taps x 32 columns
+
+struct SmemLayout {
+    uint32_t a_off, g_off, x_off, gr_off, bar_off, total, g_stage_bytes;
+    __host__ __device__ SmemLayout(uint32_t raw_stage_bytes, uint32_t g_bytes) {
+        g_stage_bytes = (g_bytes + 127u) & ~127u;
+        a_off = 0;                                   // [plane][hi | lo] x 144 rows (as in the forward kernel)
+        g_off = a_off + 4 * kPlaneBytes;             // [hi | lo] x 144 rows
+        x_off = g_off + 2 * kGPlane;
+        gr_off = x_off + kRaw * raw_stage_bytes;
+        bar_off = gr_off + kRaw * g_stage_bytes;
+        total = bar_off + 256 + 1024;
+    }
+};
+
+// MN-major SWIZZLE_128B descriptor: rows = K index (8 rows per 1024-byte atom, SBO), `lbo_bytes` between the
+// 32-element (128-byte) atoms along M/N
+__device__ __forceinline__ uint64_t make_desc_mn(const void* smem_tile, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_u32(smem_tile) & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ partial,
+                       float* __restrict__ partial_bias, Geom g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int P = g.OH * g.OW;
+    const uint32_t g_bytes = static_cast<uint32_t>(kOC * P * 4);
+    const SmemLayout L(g.raw_stage_bytes, g_bytes);
+    const uint32_t smem_u = smem_u32(smem);
+    const uint32_t a_u32 = smem_u + L.a_off, gt_u32 = smem_u + L.g_off, x_u32 = smem_u + L.x_off, gr_u32 = smem_u + L.gr_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* x_full = bars;                         // [kRaw]
+    uint64_t* x_empty = x_full + kRaw;
+    uint64_t* g_full = x_empty + kRaw;               // [kRaw]
+    uint64_t* g_empty = g_full + kRaw;
+    uint64_t* op_full = g_empty + kRaw;              // [1] operand tiles written -> MMA
+    uint64_t* op_empty = op_full + 1;                // [1] MMAs done reading
+    uint64_t* acc_full = op_empty + 1;               // [2]
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    // A and B MN-major (bits 15, 16), M = 64, N = 32
+    constexpr uint32_t kIdesc = make_idesc_tf32(64, kOC) | (1u << 15) | (1u << 16);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRaw; ++s) {
+            mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], kProducerWarps);
+            mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], kProducerWarps);
+        }
+        mbar_init(op_full, kProducerWarps);
+        mbar_init(op_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarpW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemColsW));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    const int n_local = (g.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (warp == kLoadWarpW) {
+        // ================================================================ loader: activation and gradient images
+        if (elect_one()) {
+            for (int i = 0; i < n_local; ++i) {
+                const int s = i % kRaw;
+                const uint32_t ph = ((i / kRaw) & 1) ^ 1;
+                const int64_t n = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+                mbar_wait(&x_empty[s], ph);
+                mbar_expect_tx(&x_full[s], g.img_bytes);
+                bulk_load(x_u32 + static_cast<uint32_t>(s) * g.raw_stage_bytes, reinterpret_cast<const uint8_t*>(X) + n * g.img_bytes,
+                          g.img_bytes, &x_full[s]);
+                mbar_wait(&g_empty[s], ph);
+                mbar_expect_tx(&g_full[s], g_bytes);
+                bulk_load(gr_u32 + static_cast<uint32_t>(s) * L.g_stage_bytes, G + n * (static_cast<int64_t>(kOC) * P), g_bytes, &g_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < kProducerWarps) {
+        // ================================================================ re-layout (the forward's cell rows + the dgrad's gradient rows)
+        const int q_end = kRows + g.GW + 1;
+        float bias_acc[4] = {0.f, 0.f, 0.f, 0.f};            // channels 4*warp .. 4*warp+3, this lane's rows
+        uint32_t it = 0;
+        for (int i = 0; i < n_local; ++i) {
+            const int s = i % kRaw;
+            mbar_wait(&x_full[s], (i / kRaw) & 1);
+            mbar_wait(&g_full[s], (i / kRaw) & 1);
+            const uint32_t raw_base = x_u32 + static_cast<uint32_t>(s) * g.raw_stage_bytes;
+            const uint32_t g_base = gr_u32 + static_cast<uint32_t>(s) * L.g_stage_bytes + static_cast<uint32_t>(4 * warp * P) * 4u;
+            for (int t = 0; t < g.n_tiles; ++t, ++it) {
+                // ---- loads of both operands first (activations: channel warp of each plane; gradient: chunk warp)
+                float va[2][5][4], vg[5][4];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int q = 32 * u + lane;
+                    const int cell = t * kRows + q;
+                    const int Yc = static_cast<int>((static_cast<uint32_t>(cell) * g.div_magic) >> 16);
+                    const int Xc = cell - Yc * g.GW;
+                    const bool in = q < q_end && cell < g.n_cells;
+#pragma unroll
+                    for (int plane = 0; plane < 2; ++plane) {
+                        const uint32_t ch_base = raw_base + static_cast<uint32_t>((warp + 8 * plane) * g.IH * g.IW) * 4u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int iy = 2 * Yc - 1 + (k >> 1), ix = 2 * Xc - 1 + (k & 1);
+                            const bool ok = in && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+                            va[plane][u][k] = ok ? __uint_as_float(lds32(ch_base + static_cast<uint32_t>(iy * g.IW + ix) * 4u)) : 0.0f;
+                        }
+                    }
+                    const bool gok = q < kRows && cell < g.n_cells && Yc < g.OH && Xc < g.OW;
+                    const uint32_t src = g_base + static_cast<uint32_t>(Yc * g.OW + Xc) * 4u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        vg[u][k] = gok ? __uint_as_float(lds32(src + static_cast<uint32_t>(k * P) * 4u)) : 0.0f;
+                        bias_acc[k] += vg[u][k];
+                    }
+                }
+                mbar_wait(op_empty, (it & 1) ^ 1);
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int q = 32 * u + lane;
+                    if (q < q_end && q < kSlotRows) {
+                        const uint32_t off = static_cast<uint32_t>(q * 128 + ((warp ^ (q & 7)) << 4));
+#pragma unroll
+                        for (int plane = 0; plane < 2; ++plane) {
+                            const uint32_t hi = a_u32 + static_cast<uint32_t>(plane * 2 * kPlaneBytes) + off;
+                            split_store(hi, hi + kPlaneBytes, va[plane][u]);
+                        }
+                        if (q < kRows) split_store(gt_u32 + off, gt_u32 + kGPlane + off, vg[u]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(op_full);
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&x_empty[s]); mbar_arrive(&g_empty[s]); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float sum = warp_sum(bias_acc[k]);
+            if (lane == 0) partial_bias[static_cast<int64_t>(blockIdx.x) * kOC + 4 * warp + k] = sum;
+        }
+    } else if (warp == kMmaWarpW) {
+        // ================================================================ MMA issuer
+        uint32_t it = 0;
+        for (int i = 0; i < n_local; ++i) {
+            for (int t = 0; t < g.n_tiles; ++t, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                mbar_wait(op_full, it & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint8_t* a_hi = smem + L.a_off;            // plane 0 hi; plane 1 hi is 2*kPlaneBytes further (= LBO)
+                    const uint8_t* g_hi = smem + L.g_off;
+#pragma unroll
+                    for (int tap = 0; tap < 4; ++tap) {
+                        const int shift = (tap >> 1) * g.GW + (tap & 1);
+                        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 4 * kOC + tap * kOC);
+                        const uint64_t dah = make_desc_mn(a_hi + shift * 128, 2 * kPlaneBytes);
+                        const uint64_t dal = make_desc_mn(a_hi + kPlaneBytes + shift * 128, 2 * kPlaneBytes);
+                        const uint64_t dgh = make_desc_mn(g_hi, 1024), dgl = make_desc_mn(g_hi + kGPlane, 1024);
+#pragma unroll 4
+                        for (int k = 0; k < 16; ++k) {                // K = 8 cells per MMA: one 1024-byte atom of rows
+                            const uint64_t adv = static_cast<uint64_t>(64 * k);
+                            umma_tf32(acc, dah + adv, dgh + adv, kIdesc, k ? 1u : 0u);
+                            umma_tf32(acc, dah + adv, dgl + adv, kIdesc, 1u);
+                            umma_tf32(acc, dal + adv, dgh + adv, kIdesc, 1u);
+                        }
+                    }
+                    umma_commit(op_empty);
+                    umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================================================ accumulator warps 8..15
+        // warp a: TMEM lane quarter a & 3 (valid rows: lanes 0..15 = M rows 16*(a&3) + lane), taps 2*(a>>2), 2*(a>>2)+1
+        const int a = warp - kAccWarp0;
+        const int quarter = a & 3, half = a >> 2;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        float acc[2][kOC];
+#pragma unroll
+        for (int tp = 0; tp < 2; ++tp)
+#pragma unroll
+            for (int j = 0; j < kOC; ++j) acc[tp][j] = 0.0f;
+        uint32_t it = 0;
+        for (int i = 0; i < n_local; ++i) {
+            for (int t = 0; t < g.n_tiles; ++t, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int tp = 0; tp < 2; ++tp) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + lane_base + static_cast<uint32_t>(buf * 4 * kOC + (2 * half + tp) * kOC), r);
+#pragma unroll
+                    for (int j = 0; j < kOC; ++j) acc[tp][j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+        }
+        if (lane < 16) {                                    // partial[cta][tap][m = (c,dy,dx)][oc]
+            const int m = 16 * quarter + lane;
+#pragma unroll
+            for (int tp = 0; tp < 2; ++tp) {
+                float4* dst = reinterpret_cast<float4*>(partial + ((static_cast<int64_t>(blockIdx.x) * 4 + 2 * half + tp) * 64 + m) * kOC);
+#pragma unroll
+                for (int j = 0; j < kOC / 4; ++j)
+                    dst[j] = make_float4(acc[tp][4 * j], acc[tp][4 * j + 1], acc[tp][4 * j + 2], acc[tp][4 * j + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarpW)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemColsW));
+}
+
+// dW[oc][c][2by+dy][2bx+dx] = sum_cta partial[cta][tap][m][oc] (fp64, fixed order); db[oc] = sum_cta partial_bias
+__global__ void __launch_bounds__(256)
+wgrad2_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias, int n_cta, float* __restrict__ dW,
+                     float* __restrict__ db) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;     // 4 * 64 * 32 = 8192 outputs, oc fastest
+    if (tid >= 4 * 64 * kOC) return;
+    const int oc = tid & 31, m = (tid >> 5) & 63, tap = tid >> 11;
+    double acc = 0.0;
+    for (int cta = 0; cta < n_cta; ++cta) acc += static_cast<double>(partial[((static_cast<int64_t>(cta) * 4 + tap) * 64 + m) * kOC + oc]);
+    const int by = tap >> 1, bx = tap & 1, c = m >> 2, dy = (m >> 1) & 1, dx = m & 1;
+    dW[((oc * kC + c) * 4 + 2 * by + dy) * 4 + 2 * bx + dx] = static_cast<float>(acc);
+    if (db != nullptr && tid < kOC) {
+        double b = 0.0;
+        for (int cta = 0; cta < n_cta; ++cta) b += static_cast<double>(partial_bias[cta * kOC + tid]);
+        db[tid] = static_cast<float>(b);
+    }
+}
+
+inline size_t scratch_bytes(int sms) { return static_cast<size_t>(sms) * (4 * 64 * kOC + kOC) * sizeof(float); }
+inline bool smem_ok(const Geom& g) {
+    return SmemLayout(g.raw_stage_bytes, static_cast<uint32_t>(kOC * g.OH * g.OW * 4)).total <= 232448u;
+}
+
+inline cudaError_t launch_wgrad(const float* X, const float* G, float* dW, float* db, const Geom& g, int sms, void* scratch,
+                                cudaStream_t st) {
+    const SmemLayout L(g.raw_stage_bytes, static_cast<uint32_t>(kOC * g.OH * g.OW * 4));
+    static uint32_t attr_bytes = 0;
+    if (L.total > attr_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(conv2_s2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total));
+        if (e != cudaSuccess) return e;
+        attr_bytes = L.total;
+    }
+    const int grid = g.n_img < sms ? g.n_img : sms;
+    float* partial = static_cast<float*>(scratch);
+    float* partial_bias = partial + static_cast<size_t>(grid) * 4 * 64 * kOC;
+    conv2_s2d_wgrad_kernel<<<static_cast<unsigned>(grid), kThreadsW, L.total, st>>>(X, G, partial, partial_bias, g);
+    wgrad2_reduce_kernel<<<(4 * 64 * kOC + 255) / 256, 256, 0, st>>>(partial, partial_bias, grid, dW, db);
+    return cudaGetLastError();
+}
+
+}  // namespace wg2
+
 }  // namespace c2s
 }  // namespace rl

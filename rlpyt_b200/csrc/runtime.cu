@@ -4,6 +4,7 @@
 #define RL_HAVE_SSE2 1
 #endif
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -75,7 +76,17 @@ static int64_t stream_lines_sse2(uint8_t* d, const uint8_t* s, int64_t n) {
     return i;
 }
 static int64_t stream_copy_lines(uint8_t* d, const uint8_t* s, int64_t n) {
-    static const int level = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    // Default: 128-bit stores.  Measured on the B200 host with the alternating sampler (14 env workers on the two
+    // hardware threads of 7 cores): with 512-bit non-temporal stores an env step took 2.4x as long (wait_envs
+    // 26 -> 303 us per batch step, profiles/r02_sampler_configs.txt) - wide-vector frequency licence + sibling
+    // interference cost more than the copy gained in isolation (8.0 -> 6.7 us per 28 KB frame).  RLPYT_B200_STREAM_COPY =
+    // avx2 | avx512 selects the wider paths for hosts where they pay.
+    static const int level = [] {
+        const char* e = getenv("RLPYT_B200_STREAM_COPY");
+        if (e != nullptr && strcmp(e, "avx512") == 0 && __builtin_cpu_supports("avx512f")) return 2;
+        if (e != nullptr && strcmp(e, "avx2") == 0 && __builtin_cpu_supports("avx2")) return 1;
+        return 0;
+    }();
     const int64_t i = level == 2 ? stream_lines_avx512(d, s, n) : (level == 1 ? stream_lines_avx2(d, s, n) : stream_lines_sse2(d, s, n));
     _mm_sfence();
     return i;

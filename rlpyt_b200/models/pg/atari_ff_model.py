@@ -64,6 +64,35 @@ class AtariFfModel(torch.nn.Module):
             return gemm_op.linear_tf32x3(flat, mods[0].weight, mods[0].bias, relu=True)
         return head(flat)
 
+    @torch.no_grad()
+    def forward_step(self, image, prev_action, prev_reward, distribution, uniform=None):
+        """``agent.step``'s forward: (pi, v, action).  For contiguous uint8 CUDA frames [B,C,H,W] the policy / value
+        heads, softmax and the categorical draw are ONE kernel (csrc/categorical.cu: pg_head_sample_kernel) after the
+        fused trunk; anything else takes ``forward`` + ``distribution.sample``."""
+        from rlpyt_b200 import _lib
+        from rlpyt_b200.distributions.categorical import DistInfo
+        A = self.pi.out_features
+        if (self.fused_first_layer and isinstance(image, torch.Tensor) and image.dtype == torch.uint8 and image.is_cuda
+                and image.is_contiguous() and image.dim() == 4 and A <= 32 and hasattr(distribution, "_rng_state")):
+            layers = self.conv.conv.conv
+            x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, image, None)
+            x = conv2_op.conv2_relu(x, layers[2].weight, layers[2].bias) if self.tc_second_layer else layers[2:](x)
+            h = self._head(x.view(x.shape[0], -1)).contiguous()
+            Bn, F_ = h.shape
+            pi = torch.empty((Bn, A), dtype=torch.float32, device=h.device)
+            v = torch.empty(Bn, dtype=torch.float32, device=h.device)
+            action = torch.empty(Bn, dtype=torch.int64, device=h.device)
+            if uniform is not None:
+                uniform = uniform.reshape(-1).to(device=h.device, dtype=torch.float32).contiguous()
+            state = None if uniform is not None else distribution._rng_state(h.device)
+            with torch.cuda.device(h.device):
+                _lib.call("rl_pg_head_sample_f32", _lib.ptr(h), _lib.ptr(self.pi.weight.detach()), _lib.ptr(self.pi.bias.detach()),
+                          _lib.ptr(self.value.weight.detach().view(-1)), _lib.ptr(self.value.bias.detach()), _lib.ptr(uniform),
+                          _lib.ptr(state), _lib.ptr(pi), _lib.ptr(v), _lib.ptr(action), Bn, F_, A, _lib.stream())
+            return pi, v, action
+        pi, v = self.forward(image, prev_action, prev_reward)
+        return pi, v, distribution.sample(DistInfo(prob=pi))
+
     def forward(self, image, prev_action, prev_reward):
         """[T,B,C,H,W] / [B,C,H,W] / [C,H,W] uint8 -> (pi, v) with the same leading dims."""
         if isinstance(image, LazyRows):

@@ -9,11 +9,15 @@ one ``DeviceRollout`` step engine per half operating on B-axis views of the same
 of the pinned step buffer (each half replays its own per-step CUDA graphs).  Feed-forward agents only (the
 recurrent alternating agents of the reference are outside the accelerated path).
 
-Status: written at the end of round 1 after the GPU budget was spent.  tests/test_sampler_protocol_cpu.py
-runs ``serve_actions`` of this class against the real forked worker loop with a stand-in step engine
-(alternation order, drained handshakes, observation streams equal to a host replay); the wiring of the two
-``DeviceRollout`` engines in ``initialize`` has NOT run on a GPU yet (tools/run_round2_first.sh exercises it).
+Measured on the B200 host (profiles/r02_sampler_configs.txt, 8 cores per rank): with the two groups on sibling
+hardware threads the env stepping disappears behind the device half-steps (59 ms per [128,256] batch against 76-79 ms
+for the standard sampler); tests/test_gpu_sampler.py checks its batches against a host replay of the seeded envs and
+against the reference GpuSampler's recorded batches, tests/test_sampler_protocol_cpu.py runs ``serve_actions``
+against the real forked worker loop with a stand-in step engine.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -31,8 +35,9 @@ class AlternatingSampler(GpuSampler):
 
     def initialize(self, agent, *args, **kwargs):
         if getattr(agent, "recurrent", False):
-            raise NotImplementedError("recurrent alternating agents are outside the accelerated path")
-        agent.alternating = True           # alternating_sampler.py:37: a feed-forward agent only needs the flag
+            assert getattr(agent, "alternating", False), "recurrent agents need the alternating state pair (AlternatingRecurrentAgentMixin)"
+        else:
+            agent.alternating = True       # alternating_sampler.py:37: a feed-forward agent only needs the flag
         examples = super().initialize(agent, *args, **kwargs)
         self._make_alternating_pairs()
         return examples
@@ -71,8 +76,6 @@ class AlternatingSampler(GpuSampler):
         """action_server.py:131-173 on the device step engines."""
         T = self.batch_spec.T
         wait_reset = not self.mid_batch_reset
-        import os
-        import time
         prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
         clock = time.perf_counter
         for t in range(T):
@@ -109,6 +112,7 @@ class AlternatingSampler(GpuSampler):
                 for b in ended:
                     self.agent.reset_one(idx=int(b) + sl.start)
                 ro.zero_inputs_where_done()
+            self.agent.toggle_alt()                          # value / reset do not advance the rnn state (action_server.py:168)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         for ro in self.rollouts:

@@ -97,7 +97,9 @@ class DeviceRollout:
 
     def _run(self, key, body):
         if not (self.use_graphs and self._eager_batches >= 1 and getattr(self.agent, "device", None) is not None
-                and self.agent.device.type == "cuda"):
+                and self.agent.device.type == "cuda") or getattr(self.agent, "recurrent", False):
+            # recurrent agents carry their state in fresh tensors from step to step (and zero columns of it on
+            # episode ends): not a fixed-address pattern a captured graph could replay
             body()
             return
         if not self.host.get("pinned", False):

@@ -332,6 +332,60 @@ def gen_ppo():
     _save("ppo", out)
 
 
+def gen_ppo_lstm():
+    """Two iterations of the reference's RECURRENT PPO (AtariLstmAgent, whole trajectories, minibatches over B, valid
+    mask) and one of recurrent A2C on a tiny problem, CPU.  The initial weights are stored (LSTM included)."""
+    import torch
+    from collections import namedtuple
+    from rlpyt.algos.pg.ppo import PPO
+    from rlpyt.algos.pg.a2c import A2C
+    from rlpyt.agents.pg.atari import AtariLstmAgent
+    from rlpyt.agents.pg.base import AgentInfoRnn
+    from rlpyt.distributions.categorical import DistInfo
+    from rlpyt.models.pg.atari_lstm_model import RnnState
+    from rlpyt.samplers.collections import Samples, AgentSamplesBsv, EnvSamples, BatchSpec
+    Spaces = namedtuple("Spaces", "observation action")
+    Obs = namedtuple("Obs", "shape")
+    Act = namedtuple("Act", "n")
+    out = {}
+    T, B, image_shape, A, H = 8, 6, (4, 36, 36), 5, 64
+    torch.set_num_threads(1)
+    for algo_name in ("ppo", "a2c"):
+        torch.manual_seed(5)
+        agent = AtariLstmAgent(model_kwargs=dict(fc_sizes=128, lstm_size=H))
+        agent.initialize(Spaces(Obs(image_shape), Act(A)))
+        for k, v in agent.state_dict().items():
+            out[f"{algo_name}/sd0/{k}"] = v.detach().numpy().copy()
+        algo = PPO(gae_lambda=0.95, minibatches=2, epochs=2) if algo_name == "ppo" else A2C(gae_lambda=0.95)
+        algo.initialize(agent, 4, BatchSpec(T, B), mid_batch_reset=True)
+        np.random.seed(78)
+        for itr in range(2):
+            obs, action, reward, done, value, old_prob, bv = rollout_inputs(200 + itr, T, B, image_shape, A)
+            rng = np.random.default_rng(300 + itr)
+            h0 = (rng.standard_normal((T, B, 1, H)) * 0.1).astype(np.float32)      # recorded [T,B,N,H]; only [0] is used
+            c0 = (rng.standard_normal((T, B, 1, H)) * 0.1).astype(np.float32)
+            for k, x in dict(obs=obs, action=action, reward=reward, done=done, value=value, old_prob=old_prob, bv=bv,
+                             h0=h0, c0=c0).items():
+                out[f"{algo_name}/itr{itr}/{k}"] = x
+            t = torch.from_numpy
+            all_action = torch.cat([torch.zeros(1, B, dtype=torch.int64), t(action)])
+            all_reward = torch.cat([torch.zeros(1, B), t(reward)])
+            samples = Samples(
+                agent=AgentSamplesBsv(action=all_action[1:], prev_action=all_action[:-1],
+                                      agent_info=AgentInfoRnn(dist_info=DistInfo(prob=t(old_prob)), value=t(value),
+                                                              prev_rnn_state=RnnState(h=t(h0), c=t(c0))),
+                                      bootstrap_value=t(bv)),
+                env=EnvSamples(observation=t(obs), reward=all_reward[1:], prev_reward=all_reward[:-1],
+                               done=t(done), env_info=None))
+            agent.train_mode(itr)
+            info = algo.optimize_agent(itr, samples)
+            for f in ("loss", "gradNorm", "entropy", "perplexity"):
+                out[f"{algo_name}/itr{itr}/opt_{f}"] = np.atleast_1d(np.asarray(getattr(info, f), np.float64))
+            if algo_name == "a2c":
+                break
+    _save("ppo_lstm", out)
+
+
 # --------------------------------------------------------------------------- replay
 def replay_stream(seed, n_batches, T, B, obs_shape, A, p_done):
     """Consecutive sampler batches with proper frame history (frame c of step t = frame c+1 of t-1)."""
@@ -523,7 +577,62 @@ def gen_dqn():
     _save("dqn", out)
 
 
-GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay, "dqn": gen_dqn}
+def gen_collector():
+    """The reference's own samplers (GpuSampler with cuda_idx=None, SerialSampler with the CPU collector) stepping
+    the synthetic Atari-shaped env under the deterministic policy of tests/deterministic_agent.py: every field of
+    the [T,B] batch for three consecutive iterations.  Pins oracle/collector.py and is what the GPU samplers are
+    compared with (tests/test_gpu_sampler.py)."""
+    import torch
+    sys.path.insert(0, os.path.dirname(HERE))                     # tests/
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))    # repo root (baseline.reference_arm: the env)
+    from deterministic_agent import make_agent_class
+    from baseline.reference_arm import make_env_cls
+    from rlpyt.agents.base import AgentStep
+    from rlpyt.agents.pg.base import AgentInfo
+    from rlpyt.distributions.categorical import DistInfo
+    from rlpyt.samplers.parallel.gpu.sampler import GpuSampler
+    from rlpyt.samplers.serial.sampler import SerialSampler
+    from rlpyt.samplers.parallel.cpu.collectors import CpuResetCollector
+    from rlpyt.samplers.parallel.gpu.collectors import GpuWaitResetCollector
+    Agent = make_agent_class(AgentStep, AgentInfo, DistInfo)
+    Env = make_env_cls()
+    T, B, A, image = 6, 8, 5, (4, 36, 36)
+    env_kwargs = dict(image_shape=image, n_actions=A, p_done=0.15, p_reward=0.4)
+    out = {"T": np.array([T]), "B": np.array([B]), "A": np.array([A]), "image": np.array(image), "seed": np.array([11]),
+           "p_done": np.array([0.15]), "p_reward": np.array([0.4])}
+    cases = {
+        "gpu": (GpuSampler, dict()),
+        "gpu_wait_reset": (GpuSampler, dict(CollectorCls=GpuWaitResetCollector)),
+        "serial": (SerialSampler, dict(CollectorCls=CpuResetCollector)),
+    }
+    for name, (Cls, extra) in cases.items():
+        sampler = Cls(EnvCls=Env, env_kwargs=env_kwargs, batch_T=T, batch_B=B, max_decorrelation_steps=0, **extra)
+        agent = Agent()
+        affinity = dict(cuda_idx=None, workers_cpus=[0, 1], set_affinity=False)
+        sampler.initialize(agent=agent, affinity=affinity, seed=11, bootstrap_value=True, traj_info_kwargs=dict(discount=0.99))
+        for itr in range(3):
+            agent.sample_mode(itr)
+            samples, traj_infos = sampler.obtain_samples(itr)
+            pre = f"{name}/itr{itr}/"
+            out[pre + "observation"] = samples.env.observation.numpy().copy()
+            out[pre + "reward"] = samples.env.reward.numpy().copy()
+            out[pre + "prev_reward"] = samples.env.prev_reward.numpy().copy()
+            out[pre + "done"] = samples.env.done.numpy().copy()
+            out[pre + "traj_done"] = samples.env.env_info.traj_done.numpy().copy()
+            out[pre + "game_score"] = samples.env.env_info.game_score.numpy().copy()
+            out[pre + "action"] = samples.agent.action.numpy().copy()
+            out[pre + "prev_action"] = samples.agent.prev_action.numpy().copy()
+            out[pre + "prob"] = samples.agent.agent_info.dist_info.prob.numpy().copy()
+            out[pre + "value"] = samples.agent.agent_info.value.numpy().copy()
+            out[pre + "bootstrap_value"] = samples.agent.bootstrap_value.numpy().copy()
+            out[pre + "n_traj"] = np.array([len(traj_infos)])
+            out[pre + "traj_lengths"] = np.array(sorted(int(t["Length"]) for t in traj_infos), dtype=np.int64)
+        sampler.shutdown()
+    _save("collector", out)
+
+
+GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay, "dqn": gen_dqn,
+          "collector": gen_collector, "ppo_lstm": gen_ppo_lstm}
 
 
 def main():

@@ -111,11 +111,13 @@ def test_conv2_forward_and_dgrad_vs_fp64(impl, N, plane):
     else:
         sc = torch.empty(int(lib.rl_conv2_dgrad_tc_scratch_bytes()) // 4 + 4, device="cuda")
         _lib.call("rl_conv2_dgrad_tc", _lib.ptr(go), _lib.ptr(w), _lib.ptr(gx), N, 16, IH, IW, _lib.ptr(sc), _lib.stream(), n_launch=2)
+    # fp64 reference on the HOST: cuDNN's double-precision transposed convolution takes about a minute per case here
     opad = (IH + 2 - 4) - 2 * (OH - 1), (IW + 2 - 4) - 2 * (OW - 1)
-    refx = F.conv_transpose2d(go.double(), w.double(), stride=2, padding=1, output_padding=opad)
-    sx = F.conv_transpose2d(go.double().abs(), w.double().abs(), stride=2, padding=1, output_padding=opad)
+    go_h, w_h = go.cpu().double(), w.cpu().double()
+    refx = F.conv_transpose2d(go_h, w_h, stride=2, padding=1, output_padding=opad)
+    sx = F.conv_transpose2d(go_h.abs(), w_h.abs(), stride=2, padding=1, output_padding=opad)
     assert refx.shape == gx.shape and torch.isfinite(gx).all()
-    assert float(((gx.double() - refx).abs() / sx.clamp_min(1e-30)).max()) <= 3e-6
+    assert float(((gx.cpu().double() - refx).abs() / sx.clamp_min(1e-30)).max()) <= 3e-6
 
 
 @pytest.mark.parametrize("shape", [(4, 84, 84), (4, 36, 36), (4, 104, 80)])

@@ -78,6 +78,54 @@ def test_ppo_two_iterations_vs_reference(golden, name, samples_on):
             np.testing.assert_allclose(got, want, rtol=1e-3, atol=5e-4, err_msg=k)
 
 
+@pytest.mark.parametrize("image", [(4, 84, 84), (4, 104, 80)])
+def test_ppo_first_update_full_config_vs_oracle(image):
+    """BASELINE.json configs[2] at FULL size - T=128, B=256, 8192-sample minibatches, the persistent conv kernels
+    with 55 frames per CTA, the 8192 x 512 x 3200 GEMMs, the row-gather over a 925 MB batch - not only the
+    [T=8,B=6,(4,36,36)] case of the golden file: the first minibatch update of ``PPO.optimize_agent`` against
+    oracle/ppo.py (torch-CPU fp32, pinned bit for bit to the reference by tests/test_oracle_*.py) on identical
+    samples, weights and numpy shuffle stream.  North-star tolerance: 1e-5 relative."""
+    from oracle import atari_ff
+    from oracle.ppo import PpoOracle
+    from rlpyt_b200.agents.pg.atari import AtariFfAgent
+    from rlpyt_b200.agents.pg.base import AgentInfo
+    from rlpyt_b200.algos.pg.ppo import PPO
+    from rlpyt_b200.distributions.categorical import DistInfo
+    from rlpyt_b200.samplers.collections import AgentSamplesBsv, BatchSpec, EnvSamples, Samples
+    Tf, Bf, Af = 128, 256, 6
+    rng = np.random.default_rng(5)
+    obs = rng.integers(0, 256, size=(Tf, Bf) + image, dtype=np.uint8)
+    action = rng.integers(0, Af, size=(Tf + 1, Bf))
+    reward = rng.choice(np.array([-1, 0, 1], np.float32), size=(Tf + 1, Bf), p=[.02, .96, .02]).astype(np.float32)
+    done = rng.random((Tf, Bf)) < 1 / 500.
+    value = rng.standard_normal((Tf, Bf)).astype(np.float32)
+    prob = rng.dirichlet(np.ones(Af), (Tf, Bf)).astype(np.float32)
+    bv = rng.standard_normal((1, Bf)).astype(np.float32)
+    sd0 = atari_ff.init_state_dict(image, Af, seed=3)
+    kw = dict(discount=0.99, learning_rate=1e-3, value_loss_coeff=1., entropy_loss_coeff=0.01, clip_grad_norm=1.,
+              gae_lambda=0.98, linear_lr_schedule=True, minibatches=4, epochs=4, ratio_clip=0.1)
+    oracle = PpoOracle(sd0, n_itr=100, **kw)
+    np.random.seed(123)
+    want = oracle.optimize_agent(0, obs, action[1:], reward[1:], done, value, prob, bv, max_updates=1)
+    agent = AtariFfAgent(initial_model_state_dict={k: v.clone() for k, v in sd0.items()})
+    agent.initialize(Spaces(Obs(image), Act(Af)))
+    agent.to_device(0)
+    algo = PPO(**kw)
+    algo.initialize(agent, 100, BatchSpec(Tf, Bf), mid_batch_reset=True)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    all_a, all_r = cu(action), cu(reward)
+    samples = Samples(
+        agent=AgentSamplesBsv(action=all_a[1:], prev_action=all_a[:-1],
+                              agent_info=AgentInfo(dist_info=DistInfo(prob=cu(prob)), value=cu(value)), bootstrap_value=cu(bv)),
+        env=EnvSamples(observation=cu(obs), reward=all_r[1:], prev_reward=all_r[:-1], done=cu(done), env_info=None))
+    np.random.seed(123)
+    agent.train_mode(0)
+    info = algo.optimize_agent(0, samples)
+    assert len(info.loss) == 16 and all(np.isfinite(info.loss)) and all(np.isfinite(info.gradNorm))
+    for f in ("loss", "gradNorm", "entropy", "perplexity"):
+        np.testing.assert_allclose(np.asarray(getattr(info, f))[0], want[f][0], rtol=1e-5, atol=1e-7, err_msg=f)
+
+
 def test_a2c_two_iterations_vs_reference(golden):
     from oracle import atari_ff
     from rlpyt_b200.algos.pg.a2c import A2C

@@ -52,6 +52,7 @@ def test_sampler_batch_matches_env_replay(kind, image, B, p_done, p_reward):
         for e, s in zip(envs, seeds):
             e.seed(s)
             obs.append(e.reset())
+        n_done_total = n_infos_total = 0
         for itr in range(4):
             samples, traj_infos = sampler.obtain_samples(itr)
             s_obs = samples.env.observation.cpu().numpy()
@@ -72,7 +73,11 @@ def test_sampler_batch_matches_env_replay(kind, image, B, p_done, p_reward):
                         o = e.reset()
                         n_done += 1
                     obs[b] = o
-            assert len(traj_infos) >= n_done
+            n_done_total += n_done
+            n_infos_total += len(traj_infos)
+            # completed TrajInfos travel through a multiprocessing queue (feeder thread): the ones of the last steps
+            # may surface at the next obtain_samples, never more than were completed (parallel/base.py:104-113)
+            assert kind == "serial" or n_infos_total <= n_done_total
             # aliasing: prev_action[t+1] is action[t]; prev_reward likewise (buffer.py:29-45)
             assert torch.equal(samples.agent.prev_action[1:], samples.agent.action[:-1])
             assert torch.equal(samples.env.prev_reward[1:], samples.env.reward[:-1])
@@ -169,3 +174,61 @@ def test_config1_serial_a2c_cartpole():
         info = algo.optimize_agent(itr, samples)
         assert np.isfinite(info.loss) and np.isfinite(info.gradNorm)
     assert algo.update_counter == 20
+
+
+@pytest.mark.parametrize("kind", ["gpu", "alternating", "gpu_wait_reset", "serial"])
+def test_samplers_match_reference_sampler_golden(kind, golden):
+    """Field-by-field parity with the REFERENCE's samplers (tests/golden/collector.npz: rlpyt's GpuSampler,
+    GpuSampler + GpuWaitResetCollector and SerialSampler stepping the same seeded synthetic envs under the
+    deterministic policy of tests/deterministic_agent.py, three consecutive batches): observations, actions, rewards,
+    done flags, the prev_action / prev_reward views, recorded agent_info, bootstrap values and env_info - including
+    what the agent saw as previous action / reward after an episode end (zeroed by the GPU action server, kept by
+    the CPU collector: SURVEY.md 9.5) since the policy depends on both.  The alternating sampler must produce the
+    standard GPU sampler's batch."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from deterministic_agent import make_agent_class
+    from rlpyt_b200.agents.base import AgentStep
+    from rlpyt_b200.agents.pg.base import AgentInfo
+    from rlpyt_b200.distributions.categorical import DistInfo
+    from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
+    from rlpyt_b200.samplers.collectors import GpuWaitResetCollector
+    from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler
+    from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
+    from rlpyt_b200.samplers.serial.sampler import SerialSampler
+    g = golden("collector")
+    T, B, A = int(g["T"][0]), int(g["B"][0]), int(g["A"][0])
+    image, seed = tuple(int(x) for x in g["image"]), int(g["seed"][0])
+    env_kwargs = dict(image_shape=image, n_actions=A, p_done=float(g["p_done"][0]), p_reward=float(g["p_reward"][0]))
+    cls = dict(gpu=GpuSampler, alternating=AlternatingSampler, gpu_wait_reset=GpuSampler, serial=SerialSampler)[kind]
+    extra = dict(CollectorCls=GpuWaitResetCollector) if kind == "gpu_wait_reset" else {}
+    sampler = cls(EnvCls=SyntheticAtariEnv, env_kwargs=env_kwargs, batch_T=T, batch_B=B, max_decorrelation_steps=0, **extra)
+    agent = make_agent_class(AgentStep, AgentInfo, DistInfo)()
+    sampler.initialize(agent, affinity=dict(cuda_idx=0, workers_cpus=[None, None], set_affinity=False), seed=seed,
+                       bootstrap_value=True, traj_info_kwargs=dict(discount=0.99))
+    agent.to_device(0)
+    ref = "gpu" if kind == "alternating" else kind
+    cols = slice(1, B) if kind == "serial" else slice(0, B)   # serial: env 0 also served the example step (see test_oracle_collector)
+    try:
+        for itr in range(3):
+            agent.sample_mode(itr)
+            samples, traj_infos = sampler.obtain_samples(itr)
+            pre = f"{ref}/itr{itr}/"
+            got = {
+                "observation": samples.env.observation, "reward": samples.env.reward, "prev_reward": samples.env.prev_reward,
+                "done": samples.env.done, "action": samples.agent.action, "prev_action": samples.agent.prev_action,
+                "prob": samples.agent.agent_info.dist_info.prob, "value": samples.agent.agent_info.value,
+                "bootstrap_value": samples.agent.bootstrap_value,
+                "traj_done": samples.env.env_info.traj_done, "game_score": samples.env.env_info.game_score,
+            }
+            for k, v in got.items():
+                a = v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+                want = g[pre + k]
+                assert a.shape == want.shape, (k, a.shape, want.shape)
+                assert np.array_equal(a[:, cols], want[:, cols]), (kind, itr, k)
+            if kind != "serial":
+                assert len(traj_infos) == int(g[pre + "n_traj"][0])
+                assert sorted(int(t["Length"]) for t in traj_infos) == list(g[pre + "traj_lengths"])
+    finally:
+        sampler.shutdown()

@@ -60,3 +60,17 @@ def test_sample_categorical_inverse_cdf():
     assert list(L.sample_categorical(p, [0.0, 0.5, 0.5])) == [0, 0, 2]
     assert list(L.sample_categorical(p, [0.2, 0.999, 0.0])) == [1, 0, 2]
     assert list(L.sample_categorical(p, [0.71, 0.0, 0.999])) == [2, 0, 2]
+
+
+def test_philox_known_answers():
+    """oracle/philox.py against the Random123 known-answer vectors of Philox4x32-10 (kat_vectors: counter/key all
+    zero -> 6627e8d5...; all ones -> 408f276d...; pi digits -> d16cfe09...): first output word."""
+    from oracle.philox import philox4x32_10_word0, uniforms
+    import numpy as np
+    assert int(philox4x32_10_word0([0], 0, 0)[0]) == 0x6627e8d5
+    # counter ffffffff x4, key ffffffff x2
+    assert int(philox4x32_10_word0([0xFFFFFFFFFFFFFFFF], 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF)[0]) == 0x408f276d
+    # counter 243f6a88 85a308d3 13198a2e 03707344, key a4093822 299f31d0
+    assert int(philox4x32_10_word0([0x85a308d3243f6a88], 0x0370734413198a2e, 0x299f31d0a4093822)[0]) == 0xd16cfe09
+    u = uniforms(1000, 5, 42)
+    assert u.dtype == np.float32 and float(u.min()) >= 0.0 and float(u.max()) < 1.0

@@ -148,6 +148,71 @@ static int dgrad_case(int N, int IH, int IW, bool timing) {
     return 0;
 }
 
+static int wgrad_case(int N, int IH, int IW, bool check, bool timing) {
+    if (!geom_ok(16, IH, IW)) { printf("[wgrad] %dx%d geometry not supported\n", IH, IW); return 1; }
+    Geom g = make_geom(N, IH, IW);
+    if (!wg2::smem_ok(g)) { printf("[wgrad] %dx%d shared memory does not fit\n", IH, IW); return 1; }
+    const int P = g.OH * g.OW;
+    std::vector<float> hx(static_cast<size_t>(N) * 16 * IH * IW), hg(static_cast<size_t>(N) * 32 * P);
+    for (auto& v : hx) { v = frand() * 4.0f; if (v < 0) v = 0; }
+    for (auto& v : hg) { v = frand(); if ((rnd() & 3) == 0) v = 0.0f; }
+    float *dx, *dgp, *dw, *db; void* scratch;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaMalloc(&dx, hx.size() * 4); cudaMalloc(&dgp, hg.size() * 4); cudaMalloc(&dw, 32 * 256 * 4); cudaMalloc(&db, 32 * 4);
+    cudaMalloc(&scratch, wg2::scratch_bytes(sms));
+    cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dgp, hg.data(), hg.size() * 4, cudaMemcpyHostToDevice);
+    auto launch = [&]() { return wg2::launch_wgrad(dx, dgp, dw, db, g, sms, scratch, 0); };
+    cudaError_t e = launch();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("[wgrad] N=%d %dx%d CUDA error: %s\n", N, IH, IW, cudaGetErrorString(e)); return 1; }
+    if (check) {
+        std::vector<float> gw(32 * 256), gb(32);
+        cudaMemcpy(gw.data(), dw, gw.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(gb.data(), db, 32 * 4, cudaMemcpyDeviceToHost);
+        std::vector<double> ref(32 * 256, 0.0), sc(32 * 256, 0.0), refb(32, 0.0), scb(32, 0.0);
+        for (int n = 0; n < N; ++n)
+            for (int oc = 0; oc < 32; ++oc)
+                for (int oy = 0; oy < g.OH; ++oy)
+                    for (int ox = 0; ox < g.OW; ++ox) {
+                        const double gv = hg[((static_cast<size_t>(n) * 32 + oc) * g.OH + oy) * g.OW + ox];
+                        if (gv == 0.0) continue;
+                        refb[oc] += gv; scb[oc] += std::fabs(gv);
+                        for (int c = 0; c < 16; ++c)
+                            for (int ky = 0; ky < 4; ++ky)
+                                for (int kx = 0; kx < 4; ++kx) {
+                                    const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+                                    if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;
+                                    const double t = gv * hx[((static_cast<size_t>(n) * 16 + c) * IH + iy) * IW + ix];
+                                    ref[((oc * 16 + c) * 4 + ky) * 4 + kx] += t;
+                                    sc[((oc * 16 + c) * 4 + ky) * 4 + kx] += std::fabs(t);
+                                }
+                    }
+        double mr = 0.0, mb = 0.0;
+        for (int i = 0; i < 32 * 256; ++i) mr = std::fmax(mr, std::fabs(gw[i] - ref[i]) / (sc[i] + 1e-300));
+        for (int i = 0; i < 32; ++i) mb = std::fmax(mb, std::fabs(gb[i] - refb[i]) / (scb[i] + 1e-300));
+        printf("[wgrad] N=%d %dx%d: max err/sum|g||x| = %.3e, bias %.3e -> %s\n", N, IH, IW, mr, mb, (mr <= 1e-5 && mb <= 1e-5) ? "OK" : "MISMATCH");
+    }
+    if (timing) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 3; ++i) launch();
+        cudaEventRecord(e0);
+        for (int i = 0; i < 20; ++i) launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double us = ms * 1000.0 / 20.0, bytes = static_cast<double>(N) * (16.0 * IH * IW * 4 + 32.0 * P * 4);
+        printf("[wgrad] N=%d %dx%d: %.1f us per call (kernel + reduce), %.0f GB/s of algorithmic bytes (v1 tcgen05 kernel: ~300 us at N=8192 20x20)\n", N, IH,
+               IW, us, bytes / us * 1e-3);
+    }
+    cudaFree(dx); cudaFree(dgp); cudaFree(dw); cudaFree(db); cudaFree(scratch);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const int which = argc > 1 ? atoi(argv[1]) : 1;
     if (which & 1) {
@@ -168,6 +233,14 @@ int main(int argc, char** argv) {
         dgrad_case(256, 20, 20, true);
         dgrad_case(8192, 20, 20, true);
         dgrad_case(8192, 25, 19, true);
+    }
+    if (which & 4) {
+        wgrad_case(3, 20, 20, true, false);
+        wgrad_case(301, 20, 20, true, false);
+        wgrad_case(70, 25, 19, true, false);
+        wgrad_case(9, 8, 6, true, false);
+        wgrad_case(8192, 20, 20, false, true);
+        wgrad_case(8192, 25, 19, false, true);
     }
     return 0;
 }
