@@ -38,7 +38,9 @@ def init_state_dict(image_shape, n_actions, seed=0, fc=512):
 
 def forward(sd, image):
     """image: [N,C,H,W] uint8 (or float already scaled) -> (pi [N,A], v [N])."""
-    img = image.type(torch.float)
+    # fp32 as the reference (atari_ff_model.py:50-51); a float64 state dict runs the same arithmetic in double
+    # (tests: the "exact" side when two fp32 implementations differ by their summation order)
+    img = image.type(sd["conv.conv.conv.0.weight"].dtype)
     if image.dtype == torch.uint8:
         img = img.mul_(1. / 255)                                                   # atari_ff_model.py:50-51
     x = F.relu(F.conv2d(img, sd["conv.conv.conv.0.weight"], sd["conv.conv.conv.0.bias"],

@@ -570,16 +570,23 @@ struct SmemLayout {
     }
 };
 
-// MN-major SWIZZLE_128B descriptor: rows = K index (8 rows per 1024-byte atom, SBO), `lbo_bytes` between the
-// 32-element (128-byte) atoms along M/N
+// MN-major descriptor for 32-bit operands: layout SWIZZLE_128B_BASE32B (cute::UMMA::LayoutType 1, Swizzle<2,5,2>:
+// the 32-byte unit index of a 128-byte row is XORed with the row index mod 4; a K atom is 4 rows = 512 bytes, SBO).
+// The ordinary SWIZZLE_128B pattern (16-byte units, row mod 8) is only valid MN-major for 8/16-bit types - with it a
+// kind::tf32 MMA returns zeros (tools/probes/conv2_s2d_probe.cu: mn_major_probes).  `lbo_bytes` = distance between
+// the 32-element (128-byte) atoms along M/N.
 __device__ __forceinline__ uint64_t make_desc_mn(const void* smem_tile, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_u32(smem_tile) & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(1) << 61;
     return d;
+}
+// byte offset of the 16-byte chunk j (4 floats) of row q in that layout
+__device__ __forceinline__ uint32_t mn32_chunk_off(int q, int j) {
+    return static_cast<uint32_t>(q * 128 + ((((j >> 1) ^ (q & 3)) << 5) | ((j & 1) << 4)));
 }
 
 __global__ void __launch_bounds__(kThreadsW, 1)
@@ -689,7 +696,7 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
                 for (int u = 0; u < 5; ++u) {
                     const int q = 32 * u + lane;
                     if (q < q_end && q < kSlotRows) {
-                        const uint32_t off = static_cast<uint32_t>(q * 128 + ((warp ^ (q & 7)) << 4));
+                        const uint32_t off = mn32_chunk_off(q, warp);
 #pragma unroll
                         for (int plane = 0; plane < 2; ++plane) {
                             const uint32_t hi = a_u32 + static_cast<uint32_t>(plane * 2 * kPlaneBytes) + off;

@@ -76,7 +76,19 @@ class Conv2ReluTC(torch.autograd.Function):
             with torch.cuda.device(dev):
                 _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx),
                           N, C, IH, IW, _lib.ptr(scratch), _lib.stream(), n_launch=2)
-        if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc":
+        if ((ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc" and s2d_supported(C, IH, IW)
+                and ((IH + 2 - 4) // 2 + 2) * ((IW + 2 - 4) // 2 + 2) <= 128):
+            # one 128-cell tile per image (20x20 planes): both operands MN-major, K = cells (csrc/conv2_s2d.cuh wg2)
+            gw = torch.empty_like(weight)
+            gb = torch.empty(32, dtype=torch.float32, device=x.device)
+            sc = _SCRATCH.get(("wgrad_s2d", str(x.device)))
+            if sc is None:
+                sc = torch.empty(int(_lib.load().rl_conv2_wgrad_s2d_scratch_bytes()) // 4 + 4, dtype=torch.float32, device=x.device)
+                _SCRATCH[("wgrad_s2d", str(x.device))] = sc
+            with torch.cuda.device(x.device):
+                _lib.call("rl_conv2_wgrad_s2d", _lib.ptr(x), _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gb), N, C, IH, IW, _lib.ptr(sc),
+                          _lib.stream(), n_launch=2)
+        elif (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc":
             gw = torch.empty_like(weight)
             gb = torch.empty(32, dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):

@@ -32,6 +32,9 @@ def get_example_outputs(agent, env):
     agent.reset()
     agent_inputs = torchify_buffer(AgentInputs(np.asarray(o), np.asarray(a), r))
     a, agent_info = agent.step(*agent_inputs)
+    if "prev_rnn_state" in getattr(agent_info, "_fields", ()):
+        # the recurrent agent leaves the B dimension in its state: strip it, [B,N,H] -> [N,H] (buffer.py:74-77)
+        agent_info = agent_info._replace(prev_rnn_state=agent_info.prev_rnn_state[0])
     return dict(observation=np.asarray(o), reward=r, done=np.asarray(d, dtype=bool), env_info=env_info,
                 action=a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a),
                 agent_info=_to_numpy(agent_info))

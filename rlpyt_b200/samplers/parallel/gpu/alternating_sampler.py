@@ -68,28 +68,57 @@ class AlternatingSampler(GpuSampler):
             host_h = dict(step_np=host["step_np"][sl], step_pyt=host["step_pyt"][sl],
                           all_action=host["all_action"][:, sl], all_reward=host["all_reward"][:, sl],
                           pinned=host.get("pinned", False))
-            ro = DeviceRollout(self.samples[:, sl], host_h, self.agent, self.device)
+            ro = DeviceRollout(self.samples[:, sl], host_h, self.agent, self.device, stream=torch.cuda.Stream(self.device))
             ro.in_action.copy_(host_h["step_pyt"].action)
             self.rollouts.append(ro)
 
     def serve_actions(self, itr):
-        """action_server.py:131-173 on the device step engines."""
+        """action_server.py:131-173 on the device step engines.  Each half owns a CUDA stream: while half A's
+        ``agent.step`` runs, the master already takes half B's observations (their workers had A's whole turn to step)
+        and starts their H2D copy, so per env step one of the two PCIe transfers leaves the critical path."""
         T = self.batch_spec.T
         wait_reset = not self.mid_batch_reset
         prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
         clock = time.perf_counter
+        if self.device.type == "cuda":
+            current = torch.cuda.current_stream(self.device)
+            for ro in self.rollouts:
+                ro.side_stream.wait_stream(current)          # the learner's last update is ordered before this batch
+        got = [set(), set()]                                 # obs_ready handshakes already taken for each half's next event
+        uploaded = [False, False]
+
+        def take_observations(alt, block):
+            for i, sem in enumerate(self.obs_ready_pair[alt]):
+                if i not in got[alt]:
+                    if not sem.acquire(block=block):
+                        return False
+                    got[alt].add(i)
+            got[alt].clear()
+            return True
+
+        def start_upload(alt, t):
+            ro, sl = self.rollouts[alt], self.halves[alt]
+            done_now = ro.step_np.done
+            if self.mid_batch_reset and np.any(done_now):
+                for b in np.where(done_now)[0]:
+                    self.agent.reset_one(idx=int(b) + sl.start)
+            ro.upload_async(t, zero_inputs_on_done=True)
+
         for t in range(T):
             for alt in range(2):
-                ro, sl = self.rollouts[alt], self.halves[alt]
+                ro = self.rollouts[alt]
                 t0 = clock() if prof is not None else 0.0
-                for s in self.obs_ready_pair[alt]:
-                    s.acquire()                              # this half wrote obs(t), reward(t-1), done(t-1)
+                if not uploaded[alt]:
+                    take_observations(alt, True)             # this half wrote obs(t), reward(t-1), done(t-1)
+                    start_upload(alt, t)
+                uploaded[alt] = False
                 t1 = clock() if prof is not None else 0.0
-                done_now = ro.step_np.done
-                if self.mid_batch_reset and np.any(done_now):
-                    for b in np.where(done_now)[0]:
-                        self.agent.reset_one(idx=int(b) + sl.start)
-                ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
+                ro.act_async(t, blank_done_rows=wait_reset)
+                other, t_other = alt ^ 1, (t if alt == 0 else t + 1)
+                if t_other < T and take_observations(other, False):
+                    start_upload(other, t_other)             # overlaps this half's agent.step
+                    uploaded[other] = True
+                ro.wait()                                    # actions of this half are in the step buffer
                 t2 = clock() if prof is not None else 0.0
                 for s in self.act_ready_pair[alt]:
                     s.release()                              # this half steps while the other is served
@@ -103,19 +132,20 @@ class AlternatingSampler(GpuSampler):
             for s in self.obs_ready_pair[alt]:
                 s.acquire()
             ro.finish()                                      # bootstrap value of this half
-            if self.device.type == "cuda":                   # the DMA out of the step buffer must have run
-                torch.cuda.current_stream(self.device).synchronize()   # before the host zeroes it below
+            ro.wait()                                        # the DMA out of the step buffer must have run before the host zeroes it below
             if np.any(ro.step_np.done):
                 ended = np.where(ro.step_np.done)[0]
                 ro.step_np.action[ended] = 0
                 ro.step_np.reward[ended] = 0
                 for b in ended:
                     self.agent.reset_one(idx=int(b) + sl.start)
-                ro.zero_inputs_where_done()
-            self.agent.toggle_alt()                          # value / reset do not advance the rnn state (action_server.py:168)
-        if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
+                with torch.cuda.stream(ro.side_stream):
+                    ro.zero_inputs_where_done()
+            toggle = getattr(self.agent, "toggle_alt", None)  # value / reset do not advance the rnn state (action_server.py:168);
+            if toggle is not None:                           # duck-typed feed-forward agents need not define it
+                toggle()
         for ro in self.rollouts:
+            ro.wait()
             ro.end_batch()
         for s in self.sync.obs_ready:
             assert not s.acquire(block=False)                # drained (action_server.py:170-173)

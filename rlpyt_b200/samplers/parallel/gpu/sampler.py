@@ -36,6 +36,12 @@ _mp = mp.get_context("fork")
 def sampling_process(common_kwargs, worker_kwargs):
     """Worker main loop (parallel/worker.py:37-101): build envs + collector, decorrelate, then
     collect a batch every time the master passes ``barrier_in`` until ``quit``."""
+    # The child inherits every Python object of the master, CUDA handles included (graphs, streams, events of this and
+    # earlier samplers).  Freeze them: a garbage collection in the child must never finalize a CUDA object in a
+    # process that has no CUDA context (observed: the worker aborts inside cudaGraphExecDestroy, the master then waits
+    # on the start-up barrier forever).
+    import gc
+    gc.freeze()
     c, w = AttrDict(**common_kwargs), AttrDict(**worker_kwargs)
     if w.cpus is not None:
         try:
@@ -149,6 +155,8 @@ class GpuSampler(BaseSampler):
             g_env += n_envs
             self.workers.append(_mp.Process(target=sampling_process,
                                             kwargs=dict(common_kwargs=common, worker_kwargs=wk), daemon=True))
+        import gc
+        gc.collect()                                         # drop cyclic garbage (old CUDA graphs ...) here, where CUDA is valid
         for w in self.workers:
             w.start()
         if not self.host["pinned"]:  # page-lock after the fork so the children never see CUDA state
@@ -158,7 +166,14 @@ class GpuSampler(BaseSampler):
                 os.sched_setaffinity(0, affinity["master_cpus"])
             except (AttributeError, OSError):
                 pass
-        self.ctrl.barrier_out.wait()  # workers decorrelated, first observations are in the step buffer
+        try:   # workers decorrelated, first observations are in the step buffer
+            self.ctrl.barrier_out.wait(timeout=300)
+        except Exception as e:  # noqa: BLE001 - a worker that died during start-up must not hang the job
+            dead = [i for i, w in enumerate(self.workers) if not w.is_alive()]
+            for w in self.workers:
+                if w.is_alive():
+                    w.terminate()
+            raise RuntimeError(f"sampler workers did not come up (dead: {dead})") from e
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
         self.profile = dict(wait_envs_s=0.0, device_step_s=0.0, release_s=0.0, steps=0)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)
@@ -184,10 +199,20 @@ class GpuSampler(BaseSampler):
         return self.eval_collector.collect_evaluation(itr)
 
     def shutdown(self):
+        """Ask the workers to leave at the next batch boundary.  If the master died in the middle of a batch the workers
+        are parked on their action semaphores and will never reach the barrier: time out and terminate them instead of
+        hanging the caller (a failed run must cost seconds, not the job's wall-clock limit)."""
+        import threading
         self.ctrl.quit.value = True
-        self.ctrl.barrier_in.wait()
+        try:
+            self.ctrl.barrier_in.wait(timeout=10)
+        except threading.BrokenBarrierError:
+            pass
         for w in self.workers:
-            w.join(timeout=10)
+            w.join(timeout=5)
+            if w.is_alive():
+                w.terminate()
+                w.join(timeout=5)
         torch.cuda.synchronize(self.device)
         if self.host.get("pinned"):
             for a in self.host["step_np"]:

@@ -14,9 +14,10 @@ import torch
 
 class DeviceRollout:
 
-    def __init__(self, samples, host, agent, device):
+    def __init__(self, samples, host, agent, device, stream=None):
         self.samples, self.host, self.agent = samples, host, agent
         self.device = device
+        self.side_stream = stream       # alternating sampler: one stream per half, so one half's H2D overlaps the other's compute
         self.step_np, self.step_pyt = host["step_np"], host["step_pyt"]
         self.all_action, self.all_reward = host["all_action"], host["all_reward"]
         B = self.step_np.action.shape[0]
@@ -96,6 +97,12 @@ class DeviceRollout:
         self.bootstrap(obs_dev)
 
     def _run(self, key, body):
+        if self.side_stream is not None:
+            with torch.cuda.stream(self.side_stream):
+                return self._run_on_current(key, body)
+        return self._run_on_current(key, body)
+
+    def _run_on_current(self, key, body):
         if not (self.use_graphs and self._eager_batches >= 1 and getattr(self.agent, "device", None) is not None
                 and self.agent.device.type == "cuda") or getattr(self.agent, "recurrent", False):
             # recurrent agents carry their state in fresh tensors from step to step (and zero columns of it on
@@ -115,16 +122,31 @@ class DeviceRollout:
         if g is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.side_stream):
                 body()
             self._graphs[key] = g
         g.replay()
+
+    # ---- the same step in two launches (alternating sampler): upload_async(k) may be issued while the OTHER half's
+    # act is still running on its own stream; act_async(k) follows on this half's stream; wait() = actions on the host
+    def upload_async(self, k, zero_inputs_on_done):
+        def body():
+            self.upload(k, zero_inputs_on_done)
+            if k == 0:
+                self.begin_batch()
+        self._run(("up", k, zero_inputs_on_done), body)
+
+    def act_async(self, k, blank_done_rows=False):
+        self._run(("act", k, blank_done_rows), lambda: self.act(k, self.obs_slot(k), blank_done_rows=blank_done_rows, sync=False))
+
+    def wait(self):
+        (self.side_stream or torch.cuda.current_stream(self.device)).synchronize()
 
     def step(self, k, zero_inputs_on_done, blank_done_rows=False):
         """Event k in [0,T): observation(k) is in the step buffer -> actions are on the host on return."""
         self._run((k, zero_inputs_on_done, blank_done_rows),
                   lambda: self._step_body(k, zero_inputs_on_done, blank_done_rows))
-        torch.cuda.current_stream(self.device).synchronize()
+        self.wait()
 
     def finish(self):
         """Event T: final observation -> bootstrap value."""

@@ -23,7 +23,7 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker("timeout") is None:
-            item.add_marker(pytest.mark.timeout(420 if item.get_closest_marker("gpu") else 600))
+            item.add_marker(pytest.mark.timeout(150 if item.get_closest_marker("gpu") else 600))
 
 
 class Golden:

@@ -57,6 +57,9 @@ def make_agent_class(AgentStep, AgentInfo, DistInfo):
         def sync_shared_memory(self):
             pass
 
+        def toggle_alt(self):
+            pass
+
         def sample_mode(self, itr):
             self._mode = "sample"
 

@@ -29,13 +29,13 @@ def _import_reference():
 
         class ProgBar:  # noqa: D401 - stub
             def __init__(self, *a, **k):
-                pass
+                self.active = True
 
             def update(self, *a, **k):
                 pass
 
             def stop(self):
-                pass
+                self.active = False
         stub.ProgBar = ProgBar
         sys.modules["pyprind"] = stub
 

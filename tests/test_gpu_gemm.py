@@ -291,6 +291,40 @@ def test_conv2_wgrad_tcgen05_vs_fp64(N, plane):
         assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.abs().sum((0, 2, 3)).max())
 
 
+@pytest.mark.parametrize("N,plane", [(1, (20, 20)), (149, (20, 20)), (700, (20, 20)), (300, (25, 19)), (9, (8, 6))])
+def test_conv2_wgrad_s2d_vs_fp64(N, plane):
+    """The cell-space weight gradient (csrc/conv2_s2d.cuh wg2: both operands MN-major in the SWIZZLE_128B_BASE32B
+    layout, K = cells, M = 64 accumulators per tap promoted to fp32 per image, fixed-order reduction) against fp64 on
+    an already masked gradient: 1e-5 of the term-magnitude sum (measured ~5e-7), deterministic."""
+    import torch.nn.functional as F
+    from rlpyt_b200 import _lib
+    lib = _lib.load()
+    if not lib.rl_conv2_s2d_supported(16, plane[0], plane[1]):
+        pytest.skip("geometry not supported by the s2d kernels")
+    g = torch.Generator(device="cuda").manual_seed(N + 3)
+    x = torch.relu(torch.randn((N, 16) + plane, device="cuda", generator=g))
+    OH, OW = (plane[0] - 2) // 2 + 1, (plane[1] - 2) // 2 + 1
+    gm = (torch.randn(N, 32, OH, OW, device="cuda", generator=g) * (torch.rand(N, 32, OH, OW, device="cuda", generator=g) < 0.7)).contiguous()
+    sc = torch.empty(int(lib.rl_conv2_wgrad_s2d_scratch_bytes()) // 4 + 4, device="cuda")
+    outs = []
+    for _ in range(2):
+        gw = torch.full((32, 16, 4, 4), float("nan"), device="cuda")
+        gb = torch.full((32,), float("nan"), device="cuda")
+        _lib.call("rl_conv2_wgrad_s2d", _lib.ptr(x), _lib.ptr(gm), _lib.ptr(gw), _lib.ptr(gb), N, 16, plane[0], plane[1], _lib.ptr(sc),
+                  _lib.stream(), n_launch=2)
+        outs.append((gw, gb))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    w = torch.zeros(32, 16, 4, 4, dtype=torch.float64, device="cuda", requires_grad=True)
+    b = torch.zeros(32, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(x.double(), w, b, stride=2, padding=1).backward(gm.double())
+    wa = torch.zeros_like(w, requires_grad=True)
+    F.conv2d(x.double(), wa, None, stride=2, padding=1).backward(gm.double().abs())
+    gw, gb = outs[0]
+    assert torch.isfinite(gw).all() and torch.isfinite(gb).all()
+    assert float(((gw.double() - w.grad).abs() / wa.grad.clamp_min(1e-300)).max()) <= 1e-5
+    assert float((gb.double() - b.grad).abs().max()) <= 1e-5 * float(gm.double().abs().sum((0, 2, 3)).max())
+
+
 @pytest.mark.parametrize("shape", [(0,), (1,), (7,), (8192, 512), (33, 5, 7)])
 def test_relu_backward_bit_exact(shape):
     from rlpyt_b200.models.gemm_op import relu_backward

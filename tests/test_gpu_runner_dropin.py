@@ -32,13 +32,13 @@ def _reference_runner():
 
         class ProgBar:
             def __init__(self, *a, **k):
-                pass
+                self.active = True
 
             def update(self, *a, **k):
                 pass
 
             def stop(self):
-                pass
+                self.active = False
         stub.ProgBar = ProgBar
         sys.modules["pyprind"] = stub
     from rlpyt.runners.minibatch_rl import MinibatchRl

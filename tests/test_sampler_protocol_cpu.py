@@ -118,10 +118,20 @@ class _FakeRollout:
         self.step_np, self.rng, self.log, self.tag = step_np, rng, log, tag
         self.obs_seen = []
 
-    def step(self, t, zero_inputs_on_done, blank_done_rows=False):
+    side_stream = None
+
+    def upload_async(self, t, zero_inputs_on_done):
+        """What the real engine DMAs at this moment: the master may call this for the other half while one half's
+        agent.step is in flight - the observations must already be the ones of step t."""
         self.obs_seen.append(self.step_np.observation.copy())
+        self.log.append((self.tag, "up", t))
+
+    def act_async(self, t, blank_done_rows=False):
         self.step_np.action[:] = self.rng.integers(0, A, len(self.step_np.action))
         self.log.append((self.tag, t))
+
+    def wait(self):
+        pass
 
     def finish(self):
         self.obs_seen.append(self.step_np.observation.copy())
@@ -201,7 +211,12 @@ def test_alternating_master_loop_against_real_workers(kind):
                 p.kill()
     assert all(p.exitcode == 0 for p in workers)
     want = [(h, t) for t in range(T) for h in (0, 1)] + [(0, "finish"), (1, "finish")]
-    assert log == want
+    assert [e for e in log if len(e) == 2] == want            # strict (half 0, half 1) alternation of the agent steps
+    ups = [e for e in log if len(e) == 3]
+    assert sorted(ups) == sorted((h, "up", t) for t in range(T) for h in (0, 1))
+    for h in (0, 1):                                          # every upload precedes its own agent step
+        for t in range(T):
+            assert log.index((h, "up", t)) < log.index((h, t))
     # replay: actions of each half come from the same seeded generators, in the same order
     rngs = [np.random.default_rng(0), np.random.default_rng(1)]
     for t in range(T + 1):

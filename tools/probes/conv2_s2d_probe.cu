@@ -10,6 +10,7 @@
 #include "conv2_s2d.cuh"
 
 using namespace rl::c2s;
+using namespace rl::tc;
 
 static uint32_t g_seed = 777u;
 static uint32_t rnd() { g_seed = g_seed * 1664525u + 1013904223u; return g_seed >> 8; }
@@ -213,6 +214,106 @@ static int wgrad_case(int N, int IH, int IW, bool check, bool timing) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- MN-major tf32 semantics
+// One CTA copies a host-built shared-memory image, issues n_mma tf32 MMAs with descriptors (a_desc + i*a_step,
+// b_desc + i*b_step) relative to the 1024-aligned base, dumps the first 32 columns of all 128 TMEM lanes.
+__global__ void __launch_bounds__(128, 1)
+tf32_mma_probe_kernel(const float* __restrict__ img, int img_floats, uint64_t a_desc, uint64_t b_desc, int a_step, int b_step, int n_mma,
+                      uint32_t idesc, float* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* sm = reinterpret_cast<float*>(smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + img_floats * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < img_floats; i += blockDim.x) sm[i] = img[i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(32));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0 && lane == 0) {
+        const uint64_t base16 = static_cast<uint64_t>((smem_u32(smem) & 0x3FFFFu) >> 4);
+        for (int i = 0; i < n_mma; ++i)
+            umma_tf32(tmem, a_desc + base16 + static_cast<uint64_t>(i * a_step), b_desc + base16 + static_cast<uint64_t>(i * b_step), idesc, i > 0 ? 1u : 0u);
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[32];
+    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16), r);
+    for (int n = 0; n < 32; ++n) out[(warp * 32 + lane) * 32 + n] = __uint_as_float(r[n]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(32));
+}
+
+static void mn_major_probes() {
+    // A: two planes of [64 k-rows][32 floats] (plane p holds m in [32p, 32p+32)), MN-major; B: [64 k-rows][32 floats] MN-major.
+    // Small integers: exact in TF32.  Expected D[m][n] = sum_k A[k + shift][m] * B[k][n] over K = 8 * n_mma.
+    const int rows = 64, plane_f = rows * 32, a_off = 0, b_off = 2 * plane_f;
+    std::vector<float> img(3 * plane_f, 0.0f), Al(rows * 64), Bl(rows * 32);
+    for (auto& v : Al) v = static_cast<float>(static_cast<int>(rnd() % 15) - 7);
+    for (auto& v : Bl) v = static_cast<float>(static_cast<int>(rnd() % 15) - 7);
+    // layout_type 2: SWIZZLE_128B (16-byte units ^ row & 7), 1: SWIZZLE_128B_BASE32B (32-byte units ^ row & 3)
+    auto fill = [&](int layout_type) {
+        for (int k = 0; k < rows; ++k) {
+            auto col = [&](int e) { return layout_type == 2 ? (((e >> 2) ^ (k & 7)) << 2) + (e & 3) : (((e >> 3) ^ (k & 3)) << 3) + (e & 7); };
+            for (int m = 0; m < 64; ++m) img[a_off + (m >> 5) * plane_f + k * 32 + col(m & 31)] = Al[k * 64 + m];
+            for (int n = 0; n < 32; ++n) img[b_off + k * 32 + col(n)] = Bl[k * 32 + n];
+        }
+    };
+    float *d_img, *d_out;
+    cudaMalloc(&d_img, img.size() * 4); cudaMalloc(&d_out, 128 * 32 * 4);
+    const int smem_bytes = static_cast<int>(img.size() * 4) + 64 + 1024;
+    cudaFuncSetAttribute(tf32_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    int layout_type = 2;
+    auto desc = [&](uint64_t start_bytes, uint64_t lbo_bytes, uint64_t sbo_bytes) {
+        return (start_bytes >> 4) | ((lbo_bytes >> 4) << 16) | ((sbo_bytes >> 4) << 32) | (1ull << 46) | (static_cast<uint64_t>(layout_type) << 61);
+    };
+    const uint32_t idesc = make_idesc_tf32(64, 32) | (1u << 15) | (1u << 16);
+    struct V { const char* name; int layout; uint64_t a_lbo, a_sbo, b_lbo, b_sbo; };
+    const V variants[] = {{"SW128 (16B units)    A: LBO=plane SBO=1024 | B: SBO=1024", 2, static_cast<uint64_t>(plane_f) * 4, 1024, 1024, 1024},
+                          {"SW128_BASE32B        A: LBO=plane SBO=512  | B: SBO=512 ", 1, static_cast<uint64_t>(plane_f) * 4, 512, 512, 512},
+                          {"SW128_BASE32B        A: LBO=512 SBO=plane  | B: SBO=512 ", 1, 512, static_cast<uint64_t>(plane_f) * 4, 512, 512},
+                          {"SW128_BASE32B        A: LBO=plane SBO=1024 | B: SBO=1024", 1, static_cast<uint64_t>(plane_f) * 4, 1024, 1024, 1024}};
+    for (const V& v : variants) {
+        layout_type = v.layout;
+        fill(v.layout);
+        cudaMemcpy(d_img, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+        for (int n_mma : {1, 4})
+            for (int shift : {0, 11}) {
+                tf32_mma_probe_kernel<<<1, 128, smem_bytes>>>(d_img, static_cast<int>(img.size()), desc(a_off * 4 + shift * 128, v.a_lbo, v.a_sbo),
+                                                              desc(b_off * 4, v.b_lbo, v.b_sbo), 64, 64, n_mma, idesc, d_out);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("[mn] %s CUDA error: %s\n", v.name, cudaGetErrorString(e)); return; }
+                std::vector<float> h(128 * 32);
+                cudaMemcpy(h.data(), d_out, h.size() * 4, cudaMemcpyDeviceToHost);
+                int bad = 0, first = -1;
+                for (int m = 0; m < 64; ++m) {
+                    const int lane = (m >> 4) * 32 + (m & 15);                    // M = 64 accumulator: lanes 0-15, 32-47, 64-79, 96-111
+                    for (int n = 0; n < 32; ++n) {
+                        float want = 0.0f;
+                        for (int k = 0; k < 8 * n_mma; ++k) want += Al[(k + shift) * 64 + m] * Bl[k * 32 + n];
+                        if (h[lane * 32 + n] != want && bad++ == 0) first = m * 32 + n;
+                    }
+                }
+                if (bad) printf("[mn] %s n_mma=%d shift=%2d: %4d mismatches, first (m=%d,n=%d) got %g\n", v.name, n_mma, shift, bad, first / 32, first % 32,
+                                h[((first / 32 >> 4) * 32 + (first / 32 & 15)) * 32 + first % 32]);
+                else printf("[mn] %s n_mma=%d shift=%2d: OK\n", v.name, n_mma, shift);
+            }
+    }
+    cudaFree(d_img); cudaFree(d_out);
+}
+
 int main(int argc, char** argv) {
     const int which = argc > 1 ? atoi(argv[1]) : 1;
     if (which & 1) {
@@ -234,6 +335,7 @@ int main(int argc, char** argv) {
         dgrad_case(8192, 20, 20, true);
         dgrad_case(8192, 25, 19, true);
     }
+    if (which & 8) mn_major_probes();
     if (which & 4) {
         wgrad_case(3, 20, 20, true, false);
         wgrad_case(301, 20, 20, true, false);

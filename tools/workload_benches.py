@@ -104,7 +104,16 @@ def run_gae(args):
         fn = lambda: U.generalized_advantage_estimation(rs, vs, ds, bs, 0.99, 0.98, advantage_dest=advs, return_dest=rets, algo=algo)
         for _ in range(W):
             fn()
-        lat[name] = _events(fn, K) * 1e6
+        torch.cuda.synchronize()
+        # device time of ONE launch: 20 launches captured back to back in a CUDA graph (an isolated launch from Python
+        # is timed together with ~20 us of launch latency on an idle GPU)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                fn()
+        graph.replay()
+        lat[name] = _events(graph.replay, K) * 1e6 / 20
+        lat[name + "_single_call_from_python"] = _events(fn, K) * 1e6
     # e2e: the public function with HOST (numpy) arrays at the config's size: H2D + kernel + D2H inside the clock
     rng = np.random.default_rng(0)
     hr, hv = rng.standard_normal((T, Bs)).astype(np.float32), rng.standard_normal((T, Bs)).astype(np.float32)
@@ -151,6 +160,7 @@ def run_gae(args):
         "dtype": "f32", "gpu_launches": launches, "clocks": clk.summary(),
         "config_l2": "inputs_larger_than_L2 (2.3 GB per launch)",
         "latency_us_128x256": {"returns_tscan_kernel": lat["tscan"], "returns_stream_kernel": lat["stream"],
+                               "tscan_single_call_from_python": lat["tscan_single_call_from_python"],
                                "algorithmic_bytes": small_bytes},
         "e2e": {"value": small_bytes / t_host / 1e9, "unit": "GB/s", "us_per_call": t_host * 1e6,
                 "what": "generalized_advantage_estimation on pinned HOST arrays [128,256]: H2D + kernel + D2H, wall clock",
