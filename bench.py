@@ -351,6 +351,7 @@ def step_kernel_rooflines(N=8192, reps=10):
     sc_i8 = torch.empty(int(lib.rl_conv1_u8_wgrad_i8_scratch_bytes()) // 4 + 4, device="cuda")
     sc_tc = wgrad_scratch(obs.device)
     sc_dg = torch.empty(int(lib.rl_conv2_dgrad_tc_scratch_bytes()) // 4 + 4, device="cuda")
+    sc_w2 = torch.empty(int(lib.rl_conv2_wgrad_s2d_scratch_bytes()) // 4 + 4, device="cuda")
     fa = torch.randn(N, 3200, device="cuda", generator=gen)
     fb = torch.randn(512, 3200, device="cuda", generator=gen)
     C, H, W = IMAGE
@@ -377,9 +378,11 @@ def step_kernel_rooflines(N=8192, reps=10):
          (lambda: _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.ptr(sc_dg), _lib.stream(),
                             n_launch=2)),
          N * (P1 + P2), "conv2_dgrad_bytes_per_launch"),
-        ("conv_wgrad_tc_kernel<Layer2> [N=8192]",
-         lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x2), None, _lib.ptr(g2), _lib.ptr(gw2), _lib.ptr(gb2), N, 16, oh, ow,
-                           _lib.ptr(sc_tc), _lib.stream(), n_launch=2),
+        (("conv2_s2d_wgrad_kernel + reduce" if s2d else "conv_wgrad_tc_kernel<Layer2>") + " [N=8192]",
+         (lambda: _lib.call("rl_conv2_wgrad_s2d", _lib.ptr(x2), _lib.ptr(g2), _lib.ptr(gw2), _lib.ptr(gb2), N, 16, oh, ow, _lib.ptr(sc_w2),
+                            _lib.stream(), n_launch=2)) if s2d else
+         (lambda: _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x2), None, _lib.ptr(g2), _lib.ptr(gw2), _lib.ptr(gb2), N, 16, oh, ow,
+                            _lib.ptr(sc_tc), _lib.stream(), n_launch=2)),
          N * (P1 + P2), "conv2_wgrad_bytes_per_launch"),
     ]
     try:
