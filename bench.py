@@ -406,30 +406,51 @@ def step_kernel_rooflines(N=8192, reps=10):
         out.append({"kernel": name, "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(tkey), "peak_source": how,
                     "us_per_launch": t * 1e6, "algorithmic_bytes": nbytes, "launches_per_update": 1})
-    # fully connected layer: 3 GEMMs per update (forward, input gradient, weight gradient) of the same size
-    for _ in range(3):
-        gemm_tn(fa, fb)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        gemm_tn(fa, fb)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e-3)
-    t = float(np.mean(ts))
+    # fully connected layer: 3 GEMMs per update (forward, input gradient, weight gradient), 2*8192*512*3200 flops each,
+    # on the kernel the Linear op dispatches (csrc/gemm_ts.cuh, incl. the preparation of its small operand)
+    from rlpyt_b200.models import gemm_op
+    ts_impl = gemm_op._use_ts(N)
+    fg = torch.randn(N, 512, device="cuda")
+
+    def fc_fwd():
+        return gemm_op.gemm_ts(fa, fb, gemm_op.split_lo(fb), None, True) if ts_impl else gemm_tn(fa, fb)
+
+    def fc_dgrad():
+        return gemm_op.gemm_ts(fg, *gemm_op.transpose_split(fb)) if ts_impl else gemm_tn(fg, gemm_op.transpose2d(fb))
+
+    def fc_wgrad():
+        if ts_impl:
+            return gemm_op.gemm_ts(fa, *gemm_op.transpose_split(fg), a_mmajor=True, c_trans=True)
+        return gemm_tn(gemm_op.transpose2d(fg), gemm_op.transpose2d(fa))
+
     try:
         tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2
         tsrc = "measured bf16 cuBLAS TF/s / 2 (TF32 runs at half the bf16 rate)"
     except Exception:
         tf32_peak, tsrc = 1125.0, "nominal dense TF32 (B200_PROFILING.md)"
     fl = 2.0 * N * 512 * 3200
-    out.append({"kernel": "gemm_tf32x3_kernel [8192x512x3200, fp32-accurate 3xTF32]", "bound": "tensor",
-                "achieved": fl / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tf32_peak,
-                "traffic": traffic_tab.get("gemm_fc_bytes_per_launch"), "peak_source": tsrc, "us_per_launch": t * 1e6,
-                "algorithmic_flops": fl, "issued_flops": 3 * fl, "launches_per_update": 3,
-                "note": "useful fp32-equivalent flops; the 3-term split issues 3x as many on the tensor pipe"})
+    kname = "gemm_ts_kernel" if ts_impl else "gemm_tf32x3_kernel"
+    for what, fn in (("forward 8192x512x3200", fc_fwd), ("input gradient 8192x3200x512", fc_dgrad),
+                     ("weight gradient 3200x512x8192", fc_wgrad)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = float(np.mean(ts))
+        out.append({"kernel": "%s [fc %s, fp32-accurate 3xTF32, incl. operand preparation]" % (kname, what), "bound": "tensor",
+                    "achieved": fl / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tf32_peak,
+                    "issued_frac": 3 * fl / t / 1e12 / tf32_peak,
+                    "traffic": traffic_tab.get("gemm_fc_bytes_per_launch"), "peak_source": tsrc, "us_per_launch": t * 1e6,
+                    "algorithmic_flops": fl, "issued_flops": 3 * fl, "launches_per_update": 1,
+                    "note": "achieved/frac count useful fp32-equivalent flops; the 3-term split issues 3x as many on the "
+                            "tensor pipe (issued_frac)"})
     return out
 
 

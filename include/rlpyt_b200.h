@@ -206,6 +206,20 @@ int64_t rl_gemm_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float* C, int64_t M, int64_t N,
                        int64_t K, int relu, void* workspace, void* stream);
 
+/* Second version of the same product (rlpyt/models/mlp.py:30-36 forward, and the autograd backward of that
+ * torch.nn.Linear: grad_input = grad_out W, grad_weight = grad_out^T x): the A operand is fed to tcgen05.mma from
+ * tensor memory, one persistent CTA per SM.
+ *   A      [M,K] row-major, or - a_mmajor != 0 - the [K,M] row-major matrix A^T (M % 4 == 0);
+ *   B,B_lo [N,K] row-major: the operand and B - trunc_tf32(B) (rl_split_lo_f32 / rl_transpose_split_f32 write it);
+ *   C      [M,N] row-major, or - c_trans != 0 - C^T as an [N,M] row-major matrix;  bias [N], nullable.
+ * workspace: rl_gemm_ts_workspace_bytes(M,N,K) bytes (0 = none; nullable = never split K). */
+int64_t rl_gemm_ts_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int rl_gemm_ts_f32(const float* A, int a_mmajor, const float* B, const float* B_lo, const float* bias, float* C,
+                   int c_trans, int64_t M, int64_t N, int64_t K, int relu, void* workspace, void* stream);
+/* lo[i] = src[i] - trunc_tf32(src[i]);  dst = src^T ([cols,rows]) and dst_lo = dst - trunc_tf32(dst) */
+int rl_split_lo_f32(const float* src, float* lo, int64_t n, void* stream);
+int rl_transpose_split_f32(const float* src, float* dst, float* dst_lo, int64_t rows, int64_t cols, void* stream);
+
 /* ------------------------------------------------------------------ conv layers as tcgen05 implicit GEMM
  * Same contracts as rl_conv1_u8_forward (uint8 frames, optional row gather, *1/255, k8 s4, 4->16)
  * and as Conv2d(16->32, k4, s2, p1)(+bias)(+ReLU) on fp32 NCHW activations

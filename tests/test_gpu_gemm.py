@@ -34,6 +34,73 @@ def test_gemm_tf32x3_accuracy(M, N, K, bias, relu):
     assert err <= 1e-4 * float(want.abs().max() + 1e-6)
 
 
+@pytest.mark.parametrize("M,N,K,a_mmajor,c_trans", [
+    (128, 128, 64, False, False), (128, 128, 64, True, False), (128, 128, 64, False, True),
+    (200, 72, 100, False, False), (200, 72, 100, True, True),          # ragged tiles and a K tail
+    (1000, 384, 1056, False, False),                                   # several tiles per CTA, k-split
+    (256, 512, 3200, False, False),                                    # agent.step shape (k-split 6)
+    (8192, 512, 3200, False, False),                                   # fc forward
+    (8192, 3200, 512, False, False),                                   # fc input gradient
+    (3200, 512, 8192, True, True),                                     # fc weight gradient: x as it lies, gw stored directly
+])
+@pytest.mark.parametrize("bias,relu", [(False, False), (True, True)])
+def test_gemm_ts_accuracy(M, N, K, a_mmajor, c_trans, bias, relu):
+    """The TMEM-operand kernel (csrc/gemm_ts.cuh) against fp64, same budget as the first kernel."""
+    from rlpyt_b200.models.gemm_op import gemm_ts, split_lo
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    bv = torch.randn(N, device="cuda", generator=g) if bias else None
+    b_lo = split_lo(b)
+    assert torch.equal(b_lo, b - (b.view(torch.int32) & -8192).view(torch.float32))
+    y = gemm_ts(a.t().contiguous() if a_mmajor else a, b, b_lo, bv, relu, a_mmajor=a_mmajor, c_trans=c_trans)
+    if c_trans:
+        assert y.shape == (N, M)
+        y = y.t()
+    want = _ref(a, b, bv, relu)
+    scale = float((a.double().abs() @ b.double().abs().t()).max())
+    err = float((y.double() - want).abs().max())
+    assert err <= 3e-6 * scale, (err, scale)
+    assert err <= 1e-4 * float(want.abs().max() + 1e-6)
+
+
+def test_gemm_ts_is_deterministic_and_rejects_bad_pitch():
+    from rlpyt_b200 import _lib
+    from rlpyt_b200.models.gemm_op import gemm_ts, split_lo, transpose_split
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(3200, 640, device="cuda", generator=g)
+    b = torch.randn(512, 640, device="cuda", generator=g)
+    bt, bt_lo = transpose_split(b.t().contiguous())       # back to [512, 640]
+    assert torch.equal(bt, b) and torch.equal(bt_lo, split_lo(b))
+    y1, y2 = gemm_ts(a, b, bt_lo), gemm_ts(a, b, bt_lo)
+    assert torch.equal(y1, y2)
+    with pytest.raises(_lib.B200LibraryError):                     # K % 4 != 0: the TMA row pitch is not a multiple of 16 bytes
+        gemm_ts(a[:, :639].contiguous(), b[:, :639].contiguous(), bt_lo[:, :639].contiguous())
+
+
+@pytest.mark.parametrize("impl", ["ts", "ss"])
+def test_linear_autograd_both_kernels_vs_fp64(impl, monkeypatch):
+    """forward / grad_input / grad_weight / grad_bias of the Linear op on each GEMM kernel against fp64 autograd."""
+    from rlpyt_b200.models import gemm_op
+    monkeypatch.setattr(gemm_op, "GEMM_IMPL", impl)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(2048, 3200, device="cuda", generator=g)
+    w = torch.randn(512, 3200, device="cuda", generator=g) / 56
+    b = torch.randn(512, device="cuda", generator=g)
+    go = torch.randn(2048, 512, device="cuda", generator=g)
+    x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = gemm_op.linear_tf32x3(x1, w1, b1, relu=True)
+    (y * go).sum().backward()
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    pre = torch.nn.functional.linear(xd, wd, bd)
+    mask = (y.detach() > 0).double()                      # the op's own ReLU mask (ties at 0 are measure-zero but not nil)
+    (pre * mask * go.double()).sum().backward()
+    yd = pre.detach() * mask
+    assert float((y.double() - yd).abs().max()) <= 1e-5 * float(yd.abs().max())
+    for got, want in ((x1.grad, xd.grad), (w1.grad, wd.grad), (b1.grad, bd.grad)):
+        assert float((got.double() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
 def test_linear_autograd_matches_torch_fp32():
     from rlpyt_b200.models.gemm_op import linear_tf32x3
     g = torch.Generator(device="cuda").manual_seed(0)
