@@ -160,6 +160,8 @@ int rl_pow_f32_to_f64(const float* x, float exponent, double* out, int64_t n, vo
 
 /* is_weights = (1/(p+1e-6))**beta / max -> float32 (prioritized.py:68-70).  n <= 2^20. */
 int rl_is_weights_f32(const double* priority, double beta, float* out, int n, void* stream);
+/* the same with an explicit epsilon: rlpyt/replays/sequence/prioritized.py:111-113 uses (1/p)**beta, eps = 0 */
+int rl_is_weights_eps_f32(const double* priority, double beta, double eps, float* out, int n, void* stream);
 
 /* ------------------------------------------------------------------ replay batch extraction (K8)
  * NStepReturnBuffer.extract_batch + NStepFrameBuffer.extract_observation -
@@ -175,6 +177,18 @@ int rl_replay_extract(const uint8_t* frames, const int64_t* action, const float*
                       float* out_prev_reward, int64_t* out_action, float* out_return,
                       uint8_t* out_done, uint8_t* out_done_n, int64_t* out_target_prev_action,
                       float* out_target_prev_reward, void* stream);
+
+/* Sequence extraction for recurrent replay (R2D1): SequenceNStepReturnBuffer.extract_batch with
+ * SequenceNStepFrameBuffer.extract_observation - rlpyt/replays/sequence/n_step.py:68-101,
+ * rlpyt/replays/sequence/frame.py:18-50, rlpyt/utils/misc.py:38-56 (extract_sequences, incl. its placement of a
+ * negative start index).  Same storage as rl_replay_extract.  With L = seq_T + n_step <= T, outputs (time-major):
+ * all_obs [L, n, n_frames, frame_bytes] u8; all_action i64 / all_reward f32 [L, n] (start one step before T_idx);
+ * return_ f32 / done u8 / done_n u8 [seq_T, n]. */
+int rl_replay_extract_sequences(const uint8_t* frames, const int64_t* action, const float* reward, const uint8_t* done,
+                                const float* return_, const uint8_t* done_n, int64_t T, int64_t B, int64_t frame_bytes,
+                                int n_frames, int n_step, const int64_t* T_idx, const int64_t* B_idx, int64_t n,
+                                int64_t seq_T, uint8_t* out_all_obs, int64_t* out_all_action, float* out_all_reward,
+                                float* out_return, uint8_t* out_done, uint8_t* out_done_n, void* stream);
 
 /* ------------------------------------------------------------------ AtariFf first layer on uint8 frames
  * img.float().mul_(1/255) -> Conv2d(4->16, k8, s4, p0) -> ReLU : rlpyt/models/pg/atari_ff_model.py:50-53,

@@ -39,6 +39,9 @@ SIGNATURES = {
     "rl_sumtree_update_f64": (c_int, [P, c_int, P, c_int64, P, c_double, c_int64, P, P]),
     "rl_pow_f32_to_f64": (c_int, [P, c_float, P, c_int64, P]),
     "rl_is_weights_f32": (c_int, [P, c_double, P, c_int, P]),
+    "rl_is_weights_eps_f32": (c_int, [P, c_double, c_double, P, c_int, P]),
+    "rl_replay_extract_sequences": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_int64,
+                                            c_int64, P, P, P, P, P, P, P]),
     "rl_replay_extract": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_int64,
                                   P, P, P, P, P, P, P, P, P, P, P]),
     "rl_conv1_u8_forward": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),

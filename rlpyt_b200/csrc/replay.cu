@@ -38,6 +38,31 @@ struct ReplayOut {
 
 constexpr int kExtractThreads = 128;
 
+// One CTA moves one frame (hw bytes), or writes zeros when it is blanked - a blanked frame is never read.
+__device__ __forceinline__ void copy_frame(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t hw, bool blank) {
+    const bool vec = (hw % 16 == 0) && aligned_dev(dst) && aligned_dev(src);
+    if (vec) {
+        const int64_t nv = hw / 16;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        constexpr int kU = 4;  // independent 16 B loads in flight per thread (441 uint4 per 84x84 frame)
+        for (int64_t j0 = threadIdx.x; j0 < nv; j0 += kExtractThreads * kU) {
+            uint4 x[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
+                x[u] = (blank || j >= nv) ? zero : ldg_stream(reinterpret_cast<const uint4*>(src) + j);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
+                if (j < nv) stg_stream(reinterpret_cast<uint4*>(dst) + j, x[u]);
+            }
+        }
+    } else {
+        for (int64_t j = threadIdx.x; j < hw; j += kExtractThreads) dst[j] = blank ? uint8_t(0) : src[j];
+    }
+}
+
 __global__ void __launch_bounds__(kExtractThreads)
 replay_extract_kernel(ReplayView v, ReplayOut o, const int64_t* __restrict__ T_idx,
                       const int64_t* __restrict__ B_idx, int64_t n) {
@@ -57,27 +82,7 @@ replay_extract_kernel(ReplayView v, ReplayOut o, const int64_t* __restrict__ T_i
     }
     uint8_t* dst = (which == 0 ? o.obs : o.target_obs) + (i * v.nf + f) * v.hw;
     const uint8_t* src = v.frames + ((t + f) * v.B + b) * v.hw;
-    const bool vec = (v.hw % 16 == 0) && aligned_dev(dst) && aligned_dev(src);
-    if (vec) {
-        const int64_t nv = v.hw / 16;
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        constexpr int kU = 4;  // independent 16 B loads in flight per thread (441 uint4 per 84x84 frame)
-        for (int64_t j0 = threadIdx.x; j0 < nv; j0 += kExtractThreads * kU) {
-            uint4 x[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
-                x[u] = (blank || j >= nv) ? zero : ldg_stream(reinterpret_cast<const uint4*>(src) + j);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int64_t j = j0 + static_cast<int64_t>(u) * kExtractThreads;
-                if (j < nv) stg_stream(reinterpret_cast<uint4*>(dst) + j, x[u]);
-            }
-        }
-    } else {
-        for (int64_t j = threadIdx.x; j < v.hw; j += kExtractThreads) dst[j] = blank ? uint8_t(0) : src[j];
-    }
+    copy_frame(dst, src, v.hw, blank);
 
     if (f == 0 && threadIdx.x == 0) {
         const int64_t tm1 = ((t - 1) % v.T + v.T) % v.T;
@@ -94,6 +99,61 @@ replay_extract_kernel(ReplayView v, ReplayOut o, const int64_t* __restrict__ T_i
             o.target_prev_action[i] = v.action[am1];                            // n_step.py:36-37 (not zeroed)
             o.target_prev_reward[i] = v.reward[am1];
         }
+    }
+}
+
+
+// ---- sequence extraction (R2D1 replay) ---------------------------------------------------------------------------
+// Reference (restated in oracle/replay_sequence.py): rlpyt/replays/sequence/n_step.py:68-101 (extract_batch),
+// rlpyt/replays/sequence/frame.py:18-50 (observation sequences from single frames; frames of the previous episode
+// zeroed) and rlpyt/utils/misc.py:38-56 (extract_sequences).  Sample i starts at ring time t = T_idx[i], column
+// b = B_idx[i]; with L = seq_T + n_step:
+//   all_observation [L, n, nf, hw]   position j = the frame stack of ring time (t + j) % T
+//   all_action, all_reward [L, n]    sequences started at t - 1 (they begin with prev_action / prev_reward)
+//   return_, done, done_n [seq_T, n] sequences started at t
+// extract_sequences' handling of a NEGATIVE start (t - 1 = -1) is kept as it is: the first L + start positions read
+// rows 0.., the last -start positions read the ring's last rows (misc.py:49-51) - i.e. the wrapped row lands at the
+// end of the sequence, not at its beginning.
+__device__ __forceinline__ int64_t sequence_row(int64_t start, int64_t j, int64_t len, int64_t ring) {
+    if (start + len > ring) return ((start + j) % ring + ring) % ring;     // wrap at the end
+    if (start < 0) return j < len + start ? j : ring - len + j;            // misc.py:49-51
+    return start + j;
+}
+
+__global__ void __launch_bounds__(kExtractThreads)
+replay_extract_seq_frames_kernel(ReplayView v, uint8_t* __restrict__ out, const int64_t* __restrict__ T_idx,
+                                 const int64_t* __restrict__ B_idx, int64_t n, int64_t L) {
+    const int64_t blk = blockIdx.x;
+    const int c = static_cast<int>(blk % v.nf);
+    const int64_t i = (blk / v.nf) % n;
+    const int64_t j = blk / (v.nf * n);
+    const int64_t b = B_idx[i];
+    const int64_t t = (T_idx[i] + j) % v.T;
+    bool blank = false;                                                     // frame.py:39-48
+    for (int k = 1; k <= v.nf - 1 - c; ++k) {
+        const int64_t tk = ((t - k) % v.T + v.T) % v.T;
+        blank = blank || (v.done[tk * v.B + b] != 0);
+    }
+    copy_frame(out + ((j * n + i) * v.nf + c) * v.hw, v.frames + ((t + c) * v.B + b) * v.hw, v.hw, blank);
+}
+
+__global__ void __launch_bounds__(256)
+replay_extract_seq_scalars_kernel(ReplayView v, const int64_t* __restrict__ T_idx, const int64_t* __restrict__ B_idx,
+                                  int64_t n, int64_t seq_T, int64_t L, int64_t* __restrict__ all_action,
+                                  float* __restrict__ all_reward, float* __restrict__ return_, uint8_t* __restrict__ done,
+                                  uint8_t* __restrict__ done_n) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= L * n) return;
+    const int64_t j = e / n, i = e % n;
+    const int64_t t = T_idx[i], b = B_idx[i];
+    const int64_t rp = sequence_row(t - 1, j, L, v.T) * v.B + b;
+    all_action[e] = v.action[rp];
+    all_reward[e] = v.reward[rp];
+    if (j < seq_T) {
+        const int64_t r = sequence_row(t, j, seq_T, v.T) * v.B + b;
+        return_[e] = v.return_[r];
+        done[e] = v.done[r];
+        done_n[e] = v.done_n[r];
     }
 }
 
@@ -124,6 +184,32 @@ int rl_replay_extract(const uint8_t* frames, const int64_t* action, const float*
     rl::replay_extract_kernel<<<static_cast<unsigned>(blocks), rl::kExtractThreads, 0, rl::as_stream(stream)>>>(
         v, o, T_idx, B_idx, n);
     return rl::check_launch("replay_extract_kernel");
+}
+
+int rl_replay_extract_sequences(const uint8_t* frames, const int64_t* action, const float* reward, const uint8_t* done,
+                                const float* return_, const uint8_t* done_n, int64_t T, int64_t B, int64_t frame_bytes,
+                                int n_frames, int n_step, const int64_t* T_idx, const int64_t* B_idx, int64_t n,
+                                int64_t seq_T, uint8_t* out_all_obs, int64_t* out_all_action, float* out_all_reward,
+                                float* out_return, uint8_t* out_done, uint8_t* out_done_n, void* stream) {
+    RL_REQUIRE(frames && action && reward && done && return_ && done_n && T_idx && B_idx, RL_EINVAL,
+               "rl_replay_extract_sequences: null input pointer");
+    RL_REQUIRE(out_all_obs && out_all_action && out_all_reward && out_return && out_done && out_done_n, RL_EINVAL,
+               "rl_replay_extract_sequences: null output pointer");
+    RL_REQUIRE(T >= 1 && B >= 1 && frame_bytes >= 1 && n_frames >= 1 && n_step >= 1 && n >= 0 && seq_T >= 1 &&
+                   seq_T + n_step <= T,
+               RL_EINVAL, "rl_replay_extract_sequences: bad extent (sequences must be shorter than the ring)");
+    if (n == 0) return RL_OK;
+    const int64_t L = seq_T + n_step;
+    rl::ReplayView v{frames, action, reward, done, return_, done_n, T, B, frame_bytes, n_frames, n_step};
+    const int64_t blocks = L * n * n_frames;
+    RL_REQUIRE(blocks < (1LL << 31), RL_EINVAL, "rl_replay_extract_sequences: batch too large");
+    rl::replay_extract_seq_frames_kernel<<<static_cast<unsigned>(blocks), rl::kExtractThreads, 0, rl::as_stream(stream)>>>(
+        v, out_all_obs, T_idx, B_idx, n, L);
+    int rc = rl::check_launch("replay_extract_seq_frames_kernel");
+    if (rc != RL_OK) return rc;
+    rl::replay_extract_seq_scalars_kernel<<<static_cast<unsigned>((L * n + 255) / 256), 256, 0, rl::as_stream(stream)>>>(
+        v, T_idx, B_idx, n, seq_T, L, out_all_action, out_all_reward, out_return, out_done, out_done_n);
+    return rl::check_launch("replay_extract_seq_scalars_kernel");
 }
 
 }  // extern "C"

@@ -162,10 +162,10 @@ __global__ void pow_f32_to_f64_kernel(const float* __restrict__ x, float exponen
 }
 
 // is_weights = (1/(p+1e-6))**beta / max(...)  -> float32   (prioritized.py:68-70)
-__global__ void is_weights_kernel(const double* __restrict__ priority, double beta, float* __restrict__ out,
+__global__ void is_weights_kernel(const double* __restrict__ priority, double beta, double eps, float* __restrict__ out,
                                   int n) {
     double mx = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, pow(1.0 / (priority[i] + 1e-6), beta));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, pow(1.0 / (priority[i] + eps), beta));
     // block max (n <= a few thousand: one block)
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -179,7 +179,7 @@ __global__ void is_weights_kernel(const double* __restrict__ priority, double be
     __syncthreads();
     const double m = red[0];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double w = pow(1.0 / (priority[i] + 1e-6), beta);
+        const double w = pow(1.0 / (priority[i] + eps), beta);
         out[i] = static_cast<float>(w / m);
     }
 }
@@ -239,7 +239,13 @@ int rl_pow_f32_to_f64(const float* x, float exponent, double* out, int64_t n, vo
 
 int rl_is_weights_f32(const double* priority, double beta, float* out, int n, void* stream) {
     RL_REQUIRE(priority && out && n >= 1, RL_EINVAL, "rl_is_weights_f32: bad argument");
-    rl::is_weights_kernel<<<1, 1024, 0, rl::as_stream(stream)>>>(priority, beta, out, n);
+    rl::is_weights_kernel<<<1, 1024, 0, rl::as_stream(stream)>>>(priority, beta, 1e-6, out, n);
+    return rl::check_launch("is_weights_kernel");
+}
+
+int rl_is_weights_eps_f32(const double* priority, double beta, double eps, float* out, int n, void* stream) {
+    RL_REQUIRE(priority && out && n >= 1 && eps >= 0.0, RL_EINVAL, "rl_is_weights_eps_f32: bad argument");
+    rl::is_weights_kernel<<<1, 1024, 0, rl::as_stream(stream)>>>(priority, beta, eps, out, n);
     return rl::check_launch("is_weights_kernel");
 }
 

@@ -18,6 +18,17 @@ def _dev(x, device):
     return x if (isinstance(x, torch.Tensor) and x.device == device) else torch.as_tensor(x).to(device)
 
 
+def _assign_rows(dst, idxs, src, device):
+    """``dst[idxs] = src`` leaf by leaf (nested namedarraytuples: e.g. ``prev_rnn_state`` = (h, c))."""
+    if dst is None:
+        return
+    if isinstance(dst, torch.Tensor):
+        dst[idxs] = _dev(src, device).to(dst.dtype)
+        return
+    for name, d in dst.items():
+        _assign_rows(d, idxs, getattr(src, name), device)
+
+
 class BaseNStepReturnBuffer(BaseReplayBuffer):
 
     def __init__(self, example, size, B, discount=1, n_step_return=1, device=None):
@@ -52,9 +63,7 @@ class BaseNStepReturnBuffer(BaseReplayBuffer):
             idxs = torch.as_tensor(np.arange(t, t + T) % self.T, device=self.device)
         else:
             idxs = slice(t, t + T)
-        for name, dst in self.samples.items():
-            if dst is not None:
-                dst[idxs] = _dev(getattr(samples, name), self.device).to(dst.dtype)
+        _assign_rows(self.samples, idxs, samples, self.device)
         self.compute_returns(T)
         if not self._buffer_full and t + T >= self.T:
             self._buffer_full = True

@@ -499,6 +499,112 @@ def gen_replay():
     _save("replay", out)
 
 
+# --------------------------------------------------------------------------- sequence replay (R2D1)
+SEQ_REPLAY_CASES = [
+    # name, seed, size, B, obs_shape, n_step, discount, sampler_T, n_batches, batch_B, batch_T, rsi, prioritized,
+    # input_priorities, input_priority_shift
+    ("seq_uni_norn", 51, 96, 4, (4, 5, 4), 3, 0.99, 6, 9, 12, 5, 0, False, False, 0),
+    ("seq_uni_rsi1", 52, 96, 4, (4, 5, 4), 2, 0.9, 6, 9, 12, 4, 1, False, False, 0),
+    ("seq_uni_rsi4", 53, 128, 4, (3, 4, 4), 3, 0.99, 8, 9, 10, 8, 4, False, False, 0),
+    ("seq_pri_rsi1", 54, 96, 4, (4, 5, 4), 3, 0.99, 6, 9, 12, 5, 1, True, False, 0),
+    ("seq_pri_rsi4_input", 55, 128, 4, (4, 4, 4), 3, 0.997, 4, 16, 8, 8, 4, True, True, 1),
+    ("seq_pri_norn", 56, 60, 3, (2, 3, 3), 1, 0.95, 5, 8, 7, 3, 0, True, False, 0),
+    ("seq_mid", 57, 2048, 8, (4, 6, 6), 5, 0.997, 16, 20, 8, 24, 8, True, True, 1),
+]
+
+
+def gen_seq_replay():
+    import torch
+    from rlpyt.replays.sequence.frame import (PrioritizedSequenceReplayFrameBuffer,
+                                              UniformSequenceReplayFrameBuffer)
+    from rlpyt.algos.dqn.dqn import SamplesToBuffer
+    from rlpyt.algos.dqn.r2d1 import SamplesToBufferRnn, PrioritiesSamplesToBuffer
+    from rlpyt.utils.collections import namedarraytuple
+    RnnState = namedarraytuple("RnnState", ["h", "c"])
+    out = {}
+    for (name, seed, size, B, obs_shape, n_step, discount, sampler_T, n_batches, batch_B, batch_T, rsi, prioritized,
+         input_pri, pri_shift) in SEQ_REPLAY_CASES:
+        example = SamplesToBuffer(observation=np.zeros(obs_shape, np.uint8), action=np.int64(0),
+                                  reward=np.float32(0), done=np.bool_(False))
+        if rsi > 0:
+            example = SamplesToBufferRnn(*example, prev_rnn_state=RnnState(h=np.zeros((1, 3), np.float32),
+                                                                           c=np.zeros((1, 3), np.float32)))
+        kw = dict(example=example, size=size, B=B, discount=discount, n_step_return=n_step, rnn_state_interval=rsi,
+                  batch_T=batch_T)
+        if prioritized:
+            buf = PrioritizedSequenceReplayFrameBuffer(alpha=0.6, beta=0.9, default_priority=1, unique=False,
+                                                       input_priorities=input_pri, input_priority_shift=pri_shift, **kw)
+        else:
+            buf = UniformSequenceReplayFrameBuffer(**kw)
+        out[f"{name}/cfg"] = np.array([seed, size, B, n_step, sampler_T, n_batches, batch_B, batch_T, rsi, int(prioritized),
+                                       int(input_pri), pri_shift])
+        out[f"{name}/obs_shape"] = np.array(obs_shape)
+        out[f"{name}/discount"] = np.array([discount])
+        out[f"{name}/T"] = np.array([buf.T])
+        np.random.seed(seed)
+        rng = np.random.default_rng(seed + 1000)
+        for i, s in enumerate(replay_stream(seed, n_batches, sampler_T, B, obs_shape, 4, 0.08)):
+            stb = SamplesToBuffer(**s)
+            if rsi > 0:
+                rnn = RnnState(h=rng.standard_normal((sampler_T, B, 1, 3)).astype(np.float32),
+                               c=rng.standard_normal((sampler_T, B, 1, 3)).astype(np.float32))
+                out[f"{name}/b{i}/rnn_h"], out[f"{name}/b{i}/rnn_c"] = rnn.h, rnn.c
+                stb = SamplesToBufferRnn(*stb, prev_rnn_state=rnn)
+            if input_pri:
+                pri = (np.abs(rng.standard_normal(B)) + 0.05).astype(np.float32)      # [B], as R2D1.compute_input_priorities
+                out[f"{name}/b{i}/input_pri"] = pri
+                stb = PrioritiesSamplesToBuffer(priorities=pri, samples=stb)
+            buf.append_samples(stb)
+            out[f"{name}/b{i}/t"] = np.array([buf.t])
+            if prioritized:
+                out[f"{name}/b{i}/root"] = np.array([buf.priority_tree.tree[0]])
+            enough = buf._buffer_full or buf.t > batch_T + n_step + max(1, obs_shape[0] - 1) + max(1, rsi)
+            if not enough or (prioritized and buf.priority_tree.tree[0] <= 0):
+                continue
+            if prioritized:
+                u = rng.random(batch_B)
+                import rlpyt.replays.sum_tree as st
+                orig = np.random.rand
+                st.np.random.rand = lambda n, _u=u: _u.copy()
+                try:
+                    batch = buf.sample_batch(batch_B)
+                finally:
+                    st.np.random.rand = orig
+                out[f"{name}/b{i}/uniforms"] = u
+                out[f"{name}/b{i}/tree_idxs"] = np.asarray(buf.priority_tree.prev_tree_idxs).copy()
+                out[f"{name}/b{i}/is_weights"] = batch.is_weights.numpy().copy()
+            else:
+                st0 = np.random.get_state()
+                batch = buf.sample_batch(batch_B)
+                np.random.set_state(st0)
+                T_idxs, B_idxs = buf.sample_idxs(batch_B, batch_T)
+                out[f"{name}/b{i}/T_idxs"], out[f"{name}/b{i}/B_idxs"] = T_idxs, B_idxs
+            for k in ("all_observation", "all_action", "all_reward", "return_", "done", "done_n"):
+                out[f"{name}/b{i}/{k}"] = getattr(batch, k).numpy().copy()
+            if rsi > 0:
+                out[f"{name}/b{i}/init_h"] = batch.init_rnn_state.h.numpy().copy()
+                out[f"{name}/b{i}/init_c"] = batch.init_rnn_state.c.numpy().copy()
+            if prioritized:
+                new_pri = np.abs(rng.standard_normal(batch_B)).astype(np.float32) + 0.01
+                out[f"{name}/b{i}/new_pri"] = new_pri
+                buf.update_batch_priorities(torch.from_numpy(new_pri))
+                out[f"{name}/b{i}/root_after"] = np.array([buf.priority_tree.tree[0]])
+        if prioritized:
+            out[f"{name}/final_tree"] = buf.priority_tree.tree.copy()
+        out[f"{name}/final_return"] = buf.samples_return_.copy()
+        out[f"{name}/final_done_n"] = buf.samples_done_n.copy()
+        if rsi > 1:
+            out[f"{name}/final_rnn_h"] = buf.samples_prev_rnn_state.h.copy()
+    # extract_sequences known answers, including the wrap-at-the-beginning placement (misc.py:49-51)
+    from rlpyt.utils.misc import extract_sequences
+    arr = np.arange(10 * 3).reshape(10, 3)
+    out["extract_kat/arr"] = arr
+    out["extract_kat/T_idxs"] = np.array([-1, 0, 7, 8, 9, -2, 3])
+    out["extract_kat/B_idxs"] = np.array([0, 1, 2, 0, 1, 2, 0])
+    out["extract_kat/out"] = extract_sequences(arr, out["extract_kat/T_idxs"], out["extract_kat/B_idxs"], 4)
+    _save("seq_replay", out)
+
+
 # --------------------------------------------------------------------------- DQN loss
 DQN_CASES = [
     # name, seed, N, A, double_dqn, prioritized, delta_clip, n_step, discount
@@ -632,7 +738,7 @@ def gen_collector():
 
 
 GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay, "dqn": gen_dqn,
-          "collector": gen_collector, "ppo_lstm": gen_ppo_lstm}
+          "collector": gen_collector, "ppo_lstm": gen_ppo_lstm, "seq_replay": gen_seq_replay}
 
 
 def main():

@@ -70,3 +70,41 @@ def drive(g, name, make_buffer, to_np=np.asarray, check_root=None):
         n_checked += 1
     assert n_checked >= 2
     return buf
+
+
+SEQ_CASES = ["seq_uni_norn", "seq_uni_rsi1", "seq_uni_rsi4", "seq_pri_rsi1", "seq_pri_rsi4_input", "seq_pri_norn", "seq_mid"]
+
+
+def seq_replay_case(g, name, make, append, sample, update):
+    """Drives one recorded stream through ``make/append/sample/update`` and compares every recorded output."""
+    (seed, size, B, n_step, sampler_T, n_batches, batch_B, batch_T, rsi, prioritized, input_pri, pri_shift) = \
+        (int(v) for v in g[f"{name}/cfg"])
+    obs_shape = tuple(int(v) for v in g[f"{name}/obs_shape"])
+    buf = make(obs_shape=obs_shape, size=size, B=B, rsi=rsi, batch_T=batch_T, discount=float(g[f"{name}/discount"][0]),
+               n_step=n_step, prioritized=bool(prioritized), input_pri=bool(input_pri), pri_shift=pri_shift)
+    assert buf.T == int(g[f"{name}/T"][0])
+    np.random.seed(seed)
+    n_sampled = 0
+    for i, s in enumerate(replay_stream(seed, n_batches, sampler_T, B, obs_shape, 4, 0.08)):
+        if rsi > 0:
+            s["prev_rnn_state"] = dict(h=g[f"{name}/b{i}/rnn_h"], c=g[f"{name}/b{i}/rnn_c"])
+        append(buf, s, g[f"{name}/b{i}/input_pri"] if input_pri else None)
+        assert buf.t == int(g[f"{name}/b{i}/t"][0])
+        if f"{name}/b{i}/all_action" not in g:
+            continue
+        n_sampled += 1
+        batch = sample(buf, batch_B, g[f"{name}/b{i}/uniforms"] if prioritized else None)
+        if prioritized:
+            assert np.array_equal(batch["is_weights"], g[f"{name}/b{i}/is_weights"]), (name, i)
+        else:
+            assert np.array_equal(batch["T_idxs"], g[f"{name}/b{i}/T_idxs"])
+            assert np.array_equal(batch["B_idxs"], g[f"{name}/b{i}/B_idxs"])
+        for k in ("all_observation", "all_action", "all_reward", "return_", "done", "done_n"):
+            assert np.array_equal(batch[k], g[f"{name}/b{i}/{k}"]), (name, i, k)
+        if rsi > 0:
+            assert np.array_equal(batch["init_rnn_state"]["h"], g[f"{name}/b{i}/init_h"])
+            assert np.array_equal(batch["init_rnn_state"]["c"], g[f"{name}/b{i}/init_c"])
+        if prioritized:
+            update(buf, g[f"{name}/b{i}/new_pri"])
+    assert n_sampled >= 5
+    return buf
