@@ -605,6 +605,106 @@ def gen_seq_replay():
     _save("seq_replay", out)
 
 
+# --------------------------------------------------------------------------- R2D1
+R2D1_CASES = [
+    # name, seed, wT, bT, n_step, B, double, prioritized, delta_clip, rsi, dueling
+    ("r2d1_double_pri", 61, 4, 6, 3, 5, True, True, None, 2, False),
+    ("r2d1_plain_uniform_huber", 62, 0, 7, 1, 4, False, False, 1.0, 0, False),
+    ("r2d1_dueling", 63, 3, 5, 2, 6, True, True, None, 1, True),
+]
+
+
+def gen_r2d1():
+    """R2D1.loss (warm-up, double-Q, value rescaling, valid masks, sequence priorities) and compute_input_priorities of the
+    reference on a tiny AtariR2d1Model, CPU: the initial weights of both networks, the sampled batch, the loss, the TD
+    errors, the priorities and the gradient of every parameter."""
+    import torch
+    from collections import namedtuple
+    from rlpyt.algos.dqn.r2d1 import R2D1
+    from rlpyt.agents.dqn.atari.atari_r2d1_agent import AtariR2d1Agent
+    from rlpyt.models.dqn.atari_r2d1_model import RnnState
+    from rlpyt.replays.sequence.prioritized import SamplesFromReplayPri
+    from rlpyt.replays.sequence.n_step import SamplesFromReplay
+    from rlpyt.samplers.collections import Samples, AgentSamples, EnvSamples
+    from rlpyt.agents.dqn.r2d1_agent import AgentInfo
+    Spaces = namedtuple("Spaces", "observation action")
+    Obs = namedtuple("Obs", "shape")
+    Act = namedtuple("Act", "n")
+    out = {}
+    image_shape, A, H = (4, 36, 36), 5, 16
+    torch.set_num_threads(1)
+    for (name, seed, wT, bT, n, B, double, prioritized, delta_clip, rsi, dueling) in R2D1_CASES:
+        torch.manual_seed(seed)
+        agent = AtariR2d1Agent(model_kwargs=dict(channels=[4, 8, 8], fc_size=32, lstm_size=H, head_size=16, dueling=dueling))
+        agent.initialize(Spaces(Obs(image_shape), Act(A)))
+        with torch.no_grad():                                     # make the target network differ from the online one
+            for p_ in agent.target_model.parameters():
+                p_.add_(0.05 * torch.randn_like(p_))
+        for k, v in agent.model.state_dict().items():
+            out[f"{name}/model/{k}"] = v.detach().numpy().copy()
+        for k, v in agent.target_model.state_dict().items():
+            out[f"{name}/target/{k}"] = v.detach().numpy().copy()
+        algo = R2D1(discount=0.99, batch_T=bT, batch_B=B, warmup_T=wT, store_rnn_state_interval=rsi, n_step_return=n,
+                    double_dqn=double, prioritized_replay=prioritized, delta_clip=delta_clip, pri_eta=0.9,
+                    input_priority_shift=0 if rsi == 0 else None)
+        algo.agent = agent
+        rng = np.random.default_rng(seed)
+        L = wT + bT + n
+        batch = dict(
+            all_observation=rng.integers(0, 256, size=(L, B) + image_shape, dtype=np.uint8),
+            all_action=rng.integers(0, A, size=(L, B)).astype(np.int64),
+            all_reward=(rng.standard_normal((L, B)) * 3).astype(np.float32),        # beyond +-1: the value rescaling matters
+            return_=(rng.standard_normal((wT + bT, B)) * 4).astype(np.float32),
+            done=rng.random((wT + bT, B)) < 0.08,
+            done_n=rng.random((wT + bT, B)) < 0.15,
+            init_h=(rng.standard_normal((B, 1, H)) * 0.3).astype(np.float32),
+            init_c=(rng.standard_normal((B, 1, H)) * 0.3).astype(np.float32),
+            is_weights=(rng.random(B) * 0.8 + 0.2).astype(np.float32),
+        )
+        if wT > 0:
+            batch["done"][wT - 1, 1] = True                        # a trajectory that ends inside the warm-up (state reset)
+        batch["done"][wT + 2, 0] = True                            # and one inside the training segment (valid mask)
+        cfg = np.array([seed, wT, bT, n, B, int(double), int(prioritized), -1.0 if delta_clip is None else delta_clip, rsi,
+                        int(dueling), A, H])
+        out[f"{name}/cfg"] = cfg
+        for k, v in batch.items():
+            if k != "all_observation":      # the first draw of default_rng(seed): the test regenerates it (fixture size)
+                out[f"{name}/batch/{k}"] = v
+        out[f"{name}/batch/all_observation_sum"] = np.array([batch["all_observation"].astype(np.int64).sum()])
+        t = torch.from_numpy
+        init = None if rsi == 0 else RnnState(h=t(batch["init_h"]), c=t(batch["init_c"]))
+        base = SamplesFromReplay(all_observation=t(batch["all_observation"]), all_action=t(batch["all_action"]),
+                                 all_reward=t(batch["all_reward"]), return_=t(batch["return_"]), done=t(batch["done"]),
+                                 done_n=t(batch["done_n"]), init_rnn_state=init)
+        samples = SamplesFromReplayPri(*base, is_weights=t(batch["is_weights"])) if prioritized else base
+        agent.train_mode(0)
+        loss, td, pri = algo.loss(samples)
+        loss.backward()
+        out[f"{name}/loss"] = np.array([loss.item()], np.float64)
+        out[f"{name}/td_abs_errors"] = td.numpy().copy()
+        out[f"{name}/priorities"] = pri.detach().numpy().copy()
+        for k, p_ in agent.model.named_parameters():
+            out[f"{name}/grad/{k}"] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).numpy().copy()
+        # input priorities of a fresh sampler batch
+        Ts = 9
+        q = (rng.standard_normal((Ts, B, A)) * 2).astype(np.float32)
+        act = rng.integers(0, A, size=(Ts, B)).astype(np.int64)
+        rew = (rng.standard_normal((Ts, B)) * 2).astype(np.float32)
+        dn = rng.random((Ts, B)) < 0.1
+        smp = Samples(agent=AgentSamples(action=t(act), prev_action=t(act), agent_info=AgentInfo(q=t(q), prev_rnn_state=None)),
+                      env=EnvSamples(observation=None, reward=t(rew), prev_reward=t(rew), done=t(dn), env_info=None))
+        out[f"{name}/input/q"], out[f"{name}/input/action"] = q, act
+        out[f"{name}/input/reward"], out[f"{name}/input/done"] = rew, dn
+        if n > 1:      # (with n_step_return == 1 the reference's shapes do not line up, r2d1.py:216-219)
+            out[f"{name}/input/priorities"] = np.asarray(algo.compute_input_priorities(smp)).copy()
+    x = torch.tensor([-300., -7.5, -1., -1e-3, 0., 1e-3, 0.5, 1., 12., 4000.])
+    algo = R2D1()
+    out["value_scale/x"] = x.numpy()
+    out["value_scale/h"] = algo.value_scale(x).numpy()
+    out["value_scale/h_inv"] = algo.inv_value_scale(x).numpy()
+    _save("r2d1", out)
+
+
 # --------------------------------------------------------------------------- DQN loss
 DQN_CASES = [
     # name, seed, N, A, double_dqn, prioritized, delta_clip, n_step, discount
@@ -738,7 +838,7 @@ def gen_collector():
 
 
 GROUPS = {"returns": gen_returns, "loss": gen_loss, "ppo": gen_ppo, "replay": gen_replay, "dqn": gen_dqn,
-          "collector": gen_collector, "ppo_lstm": gen_ppo_lstm, "seq_replay": gen_seq_replay}
+          "collector": gen_collector, "ppo_lstm": gen_ppo_lstm, "seq_replay": gen_seq_replay, "r2d1": gen_r2d1}
 
 
 def main():
