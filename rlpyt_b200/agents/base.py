@@ -1,6 +1,7 @@
 """Agent base class: glue between sampler, network and algorithm (host-side mirror of
-``rlpyt/agents/base.py:17-246`` plus the recurrent-state mixins of :252-371; the async machinery of the
-reference is out of scope).
+``rlpyt/agents/base.py:17-246`` plus the recurrent-state mixins of :252-371; the asynchronous-mode methods
+``async_cpu`` / ``send_shared_memory`` / ``recv_shared_memory`` of :138-160,218-243 hand parameters from the
+optimizer's agent to the sampler's through a staging copy in HBM, see ``async_twin``).
 
 B200 design differences, all behind the unchanged method names:
 * network outputs stay on the device (the reference copies them to the CPU, agents/pg/
@@ -35,6 +36,8 @@ class BaseAgent:
         self.device = torch.device("cpu")
         self._mode = None
         self.world_size = 1
+        self._async = None             # parameter channel of asynchronous mode (async_twin)
+        self._async_role = None
 
     def __call__(self, observation, prev_action, prev_reward):
         """Training forward pass (used by the algorithm)."""
@@ -117,6 +120,61 @@ class BaseAgent:
 
     def toggle_alt(self):
         pass
+
+    # ---- asynchronous mode (agents/base.py:138-160, 218-243) ------------------------------------------------------
+    def async_cpu(self, share_memory=True):
+        """The reference builds the sampler's separate CPU model here; on this path the sampler acts on the GPU with
+        the parameter copy made by ``async_twin`` - nothing to do (kept so reference-style call sequences run)."""
+
+    def _async_tensors(self):
+        """The tensors the sampler needs from the optimizer: parameters and buffers of the acting model (agents with
+        further acting networks extend this list; target networks are the optimizer's business)."""
+        return list(self.model.state_dict().values())
+
+    def async_twin(self):
+        """-> the sampler's agent of asynchronous mode: a deep copy of this (optimizer-side) agent with its own
+        parameters on the same device, its own distribution / recurrent state / mode flag, linked to this agent by a
+        parameter channel: ``self.send_shared_memory()`` copies the trained parameters into a STAGING copy in HBM
+        (under the write lock, on the caller's stream), ``twin.recv_shared_memory()`` copies staging -> the twin's
+        parameters between batches if something new was sent (under the read lock, on the caller's stream).  Two
+        device-to-device copies of a few MB replace the reference's GPU -> shared-memory -> sampler-model round trip;
+        the staging copy is what lets the sampler finish a batch on one consistent parameter set while the optimizer
+        keeps stepping."""
+        import copy
+        from rlpyt_b200.utils.synchronize import RWLock, StreamFence
+        assert getattr(self, "_async", None) is None, "async_twin() may be called once"
+        twin = copy.deepcopy(self)
+        channel = dict(staging=[torch.empty_like(t) for t in self._async_tensors()], rw_lock=RWLock(),
+                       fence=StreamFence(self.device if self.device.type == "cuda" else None), send_count=0)
+        self._async = twin._async = channel
+        self._async_role, twin._async_role = "optimizer", "sampler"
+        twin._recv_count = 0
+        return twin
+
+    def send_shared_memory(self):
+        """agents/base.py:218-229 (optimizer side)."""
+        ch = getattr(self, "_async", None)
+        if ch is None or self._async_role != "optimizer":
+            return
+        with ch["rw_lock"].write_lock:
+            ch["fence"].before_write()
+            with torch.no_grad():
+                torch._foreach_copy_(ch["staging"], [t.detach() for t in self._async_tensors()])
+            ch["fence"].after_write()
+            ch["send_count"] += 1
+
+    def recv_shared_memory(self):
+        """agents/base.py:231-243 (sampler side)."""
+        ch = getattr(self, "_async", None)
+        if ch is None or self._async_role != "sampler":
+            return
+        with ch["rw_lock"]:
+            if self._recv_count < ch["send_count"]:
+                ch["fence"].before_read()
+                with torch.no_grad():
+                    torch._foreach_copy_([t.detach() for t in self._async_tensors()], ch["staging"])
+                ch["fence"].after_read()
+                self._recv_count = ch["send_count"]
 
 
 class RecurrentAgentMixin:

@@ -19,7 +19,8 @@ import torch
 from rlpyt_b200.algos.base import RlAlgorithm
 from rlpyt_b200.algos.dqn import loss_ops
 from rlpyt_b200.algos.optim import FlatAdam
-from rlpyt_b200.replays.non_sequence.frame import PrioritizedReplayFrameBuffer, UniformReplayFrameBuffer
+from rlpyt_b200.replays.non_sequence.frame import (AsyncPrioritizedReplayFrameBuffer, AsyncUniformReplayFrameBuffer,
+                                                   PrioritizedReplayFrameBuffer, UniformReplayFrameBuffer)
 from rlpyt_b200.utils.collections import namedarraytuple
 
 OptInfo = namedtuple("OptInfo", ["loss", "gradNorm", "tdAbsErr"])
@@ -67,6 +68,21 @@ class DQN(RlAlgorithm):
         self.initialize_replay_buffer(examples, batch_spec)
         self.optim_initialize(rank)
 
+    def async_initialize(self, agent, sampler_n_itr, batch_spec, mid_batch_reset, examples, world_size=1):
+        """dqn.py:95-109: used by the asynchronous runner only; allocates the replay buffer (its lock-and-fence
+        guarded variant, in HBM), leaves the optimizer to ``optim_initialize``; returns the buffer."""
+        self.agent = agent
+        self.n_itr = sampler_n_itr
+        self.initialize_replay_buffer(examples, batch_spec, async_=True)
+        self.mid_batch_reset = mid_batch_reset
+        self.sampler_bs = sampler_bs = batch_spec.size
+        self.world_size = world_size
+        self.updates_per_optimize = self.updates_per_sync
+        self.min_itr_learn = int(self.min_steps_learn // sampler_bs)
+        eps_itr_max = max(1, int(self.eps_steps // sampler_bs))
+        agent.set_epsilon_itr_min_max(self.min_itr_learn, eps_itr_max)
+        return self.replay_buffer
+
     def optim_initialize(self, rank=0):
         """dqn.py:111-120."""
         self.rank = rank
@@ -79,16 +95,14 @@ class DQN(RlAlgorithm):
             self.pri_beta_itr = max(1, self.pri_beta_steps // self.sampler_bs)
 
     def initialize_replay_buffer(self, examples, batch_spec, async_=False):
-        """dqn.py:122-156 (synchronous buffers; the async variants are out of scope)."""
-        if async_:
-            raise NotImplementedError("asynchronous replay is outside the accelerated path (SURVEY.md 8f row 4)")
+        """dqn.py:122-156."""
         replay_kwargs = dict(example=self.examples_to_buffer(examples), size=self.replay_size, B=batch_spec.B,
                              discount=self.discount, n_step_return=self.n_step_return)
         if self.prioritized_replay:
             replay_kwargs.update(alpha=self.pri_alpha, beta=self.pri_beta_init, default_priority=self.default_priority)
-            ReplayCls = PrioritizedReplayFrameBuffer
+            ReplayCls = AsyncPrioritizedReplayFrameBuffer if async_ else PrioritizedReplayFrameBuffer
         else:
-            ReplayCls = UniformReplayFrameBuffer
+            ReplayCls = AsyncUniformReplayFrameBuffer if async_ else UniformReplayFrameBuffer
         if self.ReplayBufferCls is not None:
             ReplayCls = self.ReplayBufferCls
         dev = getattr(self.agent, "device", None)

@@ -19,7 +19,9 @@ from rlpyt_b200.agents.base import AgentInputs
 from rlpyt_b200.algos.dqn.dqn import DQN, SamplesToBuffer
 from rlpyt_b200.algos.optim import FlatAdam
 from rlpyt_b200.algos.utils import discount_return_n_step, valid_from_done
-from rlpyt_b200.replays.sequence.frame import PrioritizedSequenceReplayFrameBuffer, UniformSequenceReplayFrameBuffer
+from rlpyt_b200.replays.sequence.frame import (AsyncPrioritizedSequenceReplayFrameBuffer,
+                                               AsyncUniformSequenceReplayFrameBuffer,
+                                               PrioritizedSequenceReplayFrameBuffer, UniformSequenceReplayFrameBuffer)
 from rlpyt_b200.utils.collections import namedarraytuple
 from rlpyt_b200.utils.tensor import select_at_indexes, valid_mean
 
@@ -66,8 +68,6 @@ class R2D1(DQN):
 
     def initialize_replay_buffer(self, examples, batch_spec, async_=False):
         """r2d1.py:88-134."""
-        if async_:
-            raise NotImplementedError("asynchronous replay is outside the accelerated path (SURVEY.md 8f row 4)")
         example_to_buffer = SamplesToBuffer(observation=examples["observation"], action=examples["action"],
                                             reward=examples["reward"], done=examples["done"])
         if self.store_rnn_state_interval > 0:
@@ -78,9 +78,9 @@ class R2D1(DQN):
         if self.prioritized_replay:
             replay_kwargs.update(alpha=self.pri_alpha, beta=self.pri_beta_init, default_priority=self.default_priority,
                                  input_priorities=self.input_priorities, input_priority_shift=self.input_priority_shift)
-            ReplayCls = PrioritizedSequenceReplayFrameBuffer
+            ReplayCls = AsyncPrioritizedSequenceReplayFrameBuffer if async_ else PrioritizedSequenceReplayFrameBuffer
         else:
-            ReplayCls = UniformSequenceReplayFrameBuffer
+            ReplayCls = AsyncUniformSequenceReplayFrameBuffer if async_ else UniformSequenceReplayFrameBuffer
         if self.ReplayBufferCls is not None:
             ReplayCls = self.ReplayBufferCls
         dev = getattr(self.agent, "device", None)

@@ -23,3 +23,15 @@ class UniformReplayFrameBuffer(UniformReplay, NStepFrameBuffer):
 
 class PrioritizedReplayFrameBuffer(PrioritizedReplay, NStepFrameBuffer):
     pass
+
+
+# Asynchronous-runner variants (rlpyt/replays/non_sequence/frame.py:33-42)
+from rlpyt_b200.replays.async_ import AsyncReplayBufferMixin  # noqa: E402
+
+
+class AsyncUniformReplayFrameBuffer(AsyncReplayBufferMixin, UniformReplayFrameBuffer):
+    pass
+
+
+class AsyncPrioritizedReplayFrameBuffer(AsyncReplayBufferMixin, PrioritizedReplayFrameBuffer):
+    pass

@@ -22,3 +22,15 @@ class UniformSequenceReplayFrameBuffer(UniformSequenceReplay, SequenceNStepFrame
 
 class PrioritizedSequenceReplayFrameBuffer(PrioritizedSequenceReplay, SequenceNStepFrameBuffer):
     pass
+
+
+# Asynchronous-runner variants (rlpyt/replays/sequence/frame.py:63-70)
+from rlpyt_b200.replays.async_ import AsyncReplayBufferMixin  # noqa: E402
+
+
+class AsyncUniformSequenceReplayFrameBuffer(AsyncReplayBufferMixin, UniformSequenceReplayFrameBuffer):
+    pass
+
+
+class AsyncPrioritizedSequenceReplayFrameBuffer(AsyncReplayBufferMixin, PrioritizedSequenceReplayFrameBuffer):
+    pass

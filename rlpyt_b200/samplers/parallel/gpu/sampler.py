@@ -100,7 +100,8 @@ class GpuSampler(BaseSampler):
         from rlpyt_b200 import _lib
         _lib.load()  # before the fork: workers use its host-side streaming copy
         env = self.EnvCls(**self.env_kwargs)
-        agent.initialize(env.spaces, share_memory=False, global_B=global_B, env_ranks=env_ranks)
+        if not getattr(self, "_agent_preinitialized", False):   # the asynchronous samplers initialize the agent in async_initialize
+            agent.initialize(env.spaces, share_memory=False, global_B=global_B, env_ranks=env_ranks)
         self.agent = agent
         self.samples, self.host, examples = build_samples_buffer(
             agent, env, self.batch_spec, bootstrap_value, device=self.device, share_host=True)

@@ -26,7 +26,8 @@ class SerialSampler(BaseSampler):
         if cuda_idx is None:
             cuda_idx = torch.cuda.current_device()
         self.device = torch.device("cuda", cuda_idx)
-        agent.initialize(self.envs[0].spaces, share_memory=False, global_B=global_B, env_ranks=env_ranks)
+        if not getattr(self, "_agent_preinitialized", False):   # the asynchronous samplers initialize the agent in async_initialize
+            agent.initialize(self.envs[0].spaces, share_memory=False, global_B=global_B, env_ranks=env_ranks)
         self.agent = agent
         self.samples, self.host, examples = build_samples_buffer(
             agent, self.envs[0], self.batch_spec, bootstrap_value, device=self.device, share_host=False)

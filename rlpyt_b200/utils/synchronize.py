@@ -140,3 +140,93 @@ class SpinThenSleepSemaphore:
         if ok:
             v[8] = taken + 1
         return ok
+
+
+class RWLock:
+    """Multiple simultaneous readers, one writer - the ``RWLock`` of ``rlpyt/utils/synchronize.py:5-36`` (same
+    surface: ``with lock:`` = read side, ``with lock.write_lock:`` = write side, ``acquire_read`` / ``release_read``
+    / ``acquire_write`` / ``release_write``) for the asynchronous runner of this package, where sampler, copier and
+    optimizer are THREADS of the one process that owns the GPU (the replay buffer and the parameters live in HBM;
+    there is nothing to put into OS shared memory), so the primitives are ``threading`` ones."""
+
+    def __init__(self):
+        import threading
+        self.write_lock = threading.Lock()
+        self._read_lock = threading.Lock()
+        self._read_count = 0
+
+    def __enter__(self):
+        self.acquire_read()
+
+    def __exit__(self, *args):
+        self.release_read()
+
+    def acquire_write(self):
+        self.write_lock.acquire()
+
+    def release_write(self):
+        self.write_lock.release()
+
+    def acquire_read(self):
+        with self._read_lock:
+            self._read_count += 1
+            if self._read_count == 1:
+                self.write_lock.acquire()
+
+    def release_read(self):
+        with self._read_lock:
+            self._read_count -= 1
+            if self._read_count == 0:
+                self.write_lock.release()
+
+
+class StreamFence:
+    """Orders device work issued by different host threads on different CUDA streams around one shared HBM object
+    (the replay ring, the parameter staging copy).  The host-side lock alone is not enough on a GPU: kernels are only
+    ENQUEUED while the lock is held.  ``after_write(stream)`` / ``after_read(stream)`` record an event on the issuing
+    stream; ``before_read(stream)`` makes the stream wait for the last write, ``before_write(stream)`` for the last
+    write and every read since.  Call them while holding the matching side of the ``RWLock``.  On a machine without
+    CUDA (host-logic tests) every method is a no-op."""
+
+    def __init__(self, device=None):
+        import threading
+        self._device = device
+        self._mutex = threading.Lock()
+        self._write_event = None
+        self._read_events = {}
+
+    @staticmethod
+    def _stream(stream, device):
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        return stream if stream is not None else torch.cuda.current_stream(device)
+
+    def before_read(self, stream=None):
+        s = self._stream(stream, self._device)
+        if s is not None and self._write_event is not None:
+            s.wait_event(self._write_event)
+
+    def after_read(self, stream=None):
+        s = self._stream(stream, self._device)
+        if s is None:
+            return
+        ev = s.record_event()
+        with self._mutex:
+            self._read_events[s.cuda_stream] = ev              # a later event on the same stream covers the earlier ones
+
+    def before_write(self, stream=None):
+        s = self._stream(stream, self._device)
+        if s is None:
+            return
+        if self._write_event is not None:
+            s.wait_event(self._write_event)
+        with self._mutex:
+            reads, self._read_events = list(self._read_events.values()), {}
+        for ev in reads:
+            s.wait_event(ev)
+
+    def after_write(self, stream=None):
+        s = self._stream(stream, self._device)
+        if s is not None:
+            self._write_event = s.record_event()
