@@ -154,6 +154,16 @@ int rl_sumtree_update_f64(double* tree, int levels, const int64_t* leaf_idx, int
                           const double* values, double value_scalar, int64_t n, double* scratch_diffs,
                           void* stream);
 
+/* update_batch_priorities of one sampled batch in one call (rlpyt/replays/sum_tree.py:130-138 with
+ * prioritized.py:73-79 folded in): leaf_idx = the n (<= 2048) tree indices of the last sample(), in ANY order,
+ * duplicates allowed (the first occurrence wins, np.unique(return_index=True)); new leaf values are either
+ * (double)(float)pow(priorities_f32, alpha) - numpy's float32 `**` - or values_f64 as given (exactly one of the two
+ * non-NULL).  The batch is sorted on the device; ancestors accumulate the differences in array order (np.add.at).
+ * scratch_sorted_idx: n int64, scratch_diffs: n doubles. */
+int rl_sumtree_update_batch(double* tree, int levels, const int64_t* leaf_idx, const float* priorities_f32, float alpha,
+                            const double* values_f64, int64_t n, int64_t* scratch_sorted_idx, double* scratch_diffs,
+                            void* stream);
+
 /* priorities ** alpha as numpy float32 pow, widened to the tree's fp64
  * (rlpyt/replays/non_sequence/prioritized.py:73-79). */
 int rl_pow_f32_to_f64(const float* x, float exponent, double* out, int64_t n, void* stream);

@@ -37,6 +37,7 @@ SIGNATURES = {
                                  c_float, c_float, P, P, P]),
     "rl_sumtree_find_f64": (c_int, [P, c_int, P, c_int64, c_int64, P, P, P, P, P, P]),
     "rl_sumtree_update_f64": (c_int, [P, c_int, P, c_int64, P, c_double, c_int64, P, P]),
+    "rl_sumtree_update_batch": (c_int, [P, c_int, P, P, c_float, P, c_int64, P, P, P]),
     "rl_pow_f32_to_f64": (c_int, [P, c_float, P, c_int64, P]),
     "rl_is_weights_f32": (c_int, [P, c_double, P, c_int, P]),
     "rl_is_weights_eps_f32": (c_int, [P, c_double, c_double, P, c_int, P]),

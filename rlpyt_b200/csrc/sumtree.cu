@@ -150,6 +150,66 @@ sumtree_propagate_kernel(double* __restrict__ tree, int levels, LeafSeg s, const
     if (lane == 0) tree[cur] = acc;
 }
 
+// ---- update_batch_priorities in two launches -------------------------------------------------------------------
+// sum_tree.py:130-138 + prioritized.py:73-79 for one sampled batch (n <= kBatchMax): ONE CTA
+//   1. sorts the batch by (leaf index, position in the batch) - bitonic sort of 64-bit composite keys in shared
+//      memory; the position tie-break makes the FIRST occurrence of a duplicated leaf lead its run, which is the one
+//      np.unique(return_index=True) keeps (:135-137);
+//   2. evaluates priority ** alpha as numpy's float32 power through fp64 (or takes fp64 values as given);
+//   3. writes the leaves and the differences (later duplicates: +0.0) in sorted order,
+// then sumtree_propagate_kernel adds the differences to the ancestors in array order as before.  The round trip
+// through torch.sort (radix sort: 4-5 launches), the gather by the permutation and the separate pow / set-leaves
+// launches of the first implementation cost ~80 us per update; this path is two launches behind one C call.
+constexpr int kBatchMax = 2048;
+constexpr int kBatchThreads = 1024;
+
+__global__ void __launch_bounds__(kBatchThreads)
+sumtree_batch_leaves_kernel(double* __restrict__ tree, const int64_t* __restrict__ leaf_idx,
+                            const float* __restrict__ pri_f32, float alpha, const double* __restrict__ values_f64,
+                            int n, int padded, int64_t* __restrict__ sorted_idx, double* __restrict__ diffs) {
+    __shared__ unsigned long long key[kBatchMax];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < padded; i += kBatchThreads)
+        key[i] = i < n ? ((static_cast<unsigned long long>(leaf_idx[i]) << 11) | static_cast<unsigned long long>(i))
+                       : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= padded; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < (padded >> 1); p += kBatchThreads) {
+                const int lo = ((p & ~(j - 1)) << 1) | (p & (j - 1));      // index with bit j clear
+                const int hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) {
+                    key[lo] = b;
+                    key[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += kBatchThreads) {
+        const unsigned long long kv = key[i];
+        const int64_t leaf = static_cast<int64_t>(kv >> 11);
+        const int pos = static_cast<int>(kv & 2047ull);
+        sorted_idx[i] = leaf;
+        const bool first = i == 0 || static_cast<int64_t>(key[i - 1] >> 11) != leaf;
+        if (!first) {                                                       // dropped by np.unique -> contributes +0.0
+            diffs[i] = 0.0;
+            continue;
+        }
+        double v;
+        if (values_f64 != nullptr) {
+            v = values_f64[pos];
+        } else {
+            const float r = static_cast<float>(pow(static_cast<double>(pri_f32[pos]), static_cast<double>(alpha)));
+            v = static_cast<double>(r);
+        }
+        diffs[i] = __dsub_rn(v, tree[leaf]);
+        tree[leaf] = v;
+    }
+}
+
 // out[i] = (double)(float)pow((double)x[i], (double)exponent): numpy's float32 `x ** alpha`
 // (rlpyt/replays/non_sequence/prioritized.py:79) evaluated through fp64 so that the fp32 result is
 // the correctly rounded one (glibc powf is correctly rounded in all but astronomically rare cases).
@@ -224,6 +284,32 @@ int rl_sumtree_update_f64(double* tree, int levels, const int64_t* leaf_idx, int
     const int64_t warps = n_chunks * (levels - 1);
     const int64_t blocks = (warps + rl::kPropWarpsPerBlock - 1) / rl::kPropWarpsPerBlock;
     RL_REQUIRE(blocks < (1LL << 31), RL_EINVAL, "rl_sumtree_update_f64: segment too large");
+    rl::sumtree_propagate_kernel<<<static_cast<unsigned>(blocks), rl::kPropWarpsPerBlock * 32, 0, st>>>(
+        tree, levels, s, scratch_diffs, n_chunks);
+    return rl::check_launch("sumtree_propagate_kernel");
+}
+
+int rl_sumtree_update_batch(double* tree, int levels, const int64_t* leaf_idx, const float* priorities_f32, float alpha,
+                            const double* values_f64, int64_t n, int64_t* scratch_sorted_idx, double* scratch_diffs,
+                            void* stream) {
+    RL_REQUIRE(tree && leaf_idx && scratch_sorted_idx && scratch_diffs, RL_EINVAL, "rl_sumtree_update_batch: null pointer");
+    RL_REQUIRE((priorities_f32 != nullptr) != (values_f64 != nullptr), RL_EINVAL,
+               "rl_sumtree_update_batch: give exactly one of priorities_f32 (with alpha) and values_f64");
+    RL_REQUIRE(levels >= 2 && levels <= 40 && n >= 0 && n <= rl::kBatchMax, RL_EINVAL,
+               "rl_sumtree_update_batch: levels=%d n=%lld (batch limit %d)", levels, (long long)n, rl::kBatchMax);
+    if (n == 0) return RL_OK;
+    cudaStream_t st = rl::as_stream(stream);
+    int padded = 32;
+    while (padded < n) padded <<= 1;
+    rl::sumtree_batch_leaves_kernel<<<1, rl::kBatchThreads, 0, st>>>(tree, leaf_idx, priorities_f32, alpha, values_f64,
+                                                                   static_cast<int>(n), padded, scratch_sorted_idx,
+                                                                   scratch_diffs);
+    int rc = rl::check_launch("sumtree_batch_leaves_kernel");
+    if (rc != RL_OK) return rc;
+    rl::LeafSeg s{scratch_sorted_idx, 0, n};
+    const int64_t n_chunks = (n + 31) / 32;
+    const int64_t warps = n_chunks * (levels - 1);
+    const int64_t blocks = (warps + rl::kPropWarpsPerBlock - 1) / rl::kPropWarpsPerBlock;
     rl::sumtree_propagate_kernel<<<static_cast<unsigned>(blocks), rl::kPropWarpsPerBlock * 32, 0, st>>>(
         tree, levels, s, scratch_diffs, n_chunks);
     return rl::check_launch("sumtree_propagate_kernel");

@@ -79,7 +79,10 @@ class PrioritizedSequenceReplay:
 
     def update_batch_priorities(self, priorities):
         """sequence/prioritized.py:117-119."""
-        self.priority_tree.update_batch_priorities(self._pow_alpha(priorities).reshape(-1))
+        if getattr(self, "pow_on_host", False):                # numpy's own float32 pow on the host (bit-for-bit replay of a recorded stream)
+            self.priority_tree.update_batch_priorities(self._pow_alpha(priorities).reshape(-1))
+        else:                                                  # pow folded into the tree update (csrc/sumtree.cu)
+            self.priority_tree.update_batch_priorities(priorities, alpha=self.alpha)
 
 
 class PrioritizedSequenceReplayBuffer(PrioritizedSequenceReplay, SequenceNStepReturnBuffer):

@@ -10,6 +10,15 @@ import torch
 from rlpyt_b200 import _lib
 
 
+def _pow_alpha_f64(priorities, alpha, device):
+    """``priorities ** alpha`` as numpy float32 pow, widened to fp64 (prioritized.py:49,79) - device kernel."""
+    p = torch.as_tensor(priorities).to(device, dtype=torch.float32).contiguous()
+    out = torch.empty(p.shape, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        _lib.call("rl_pow_f32_to_f64", _lib.ptr(p), float(np.float32(alpha)), _lib.ptr(out), p.numel(), _lib.stream())
+    return out
+
+
 class SumTree:
 
     async_ = False
@@ -151,11 +160,36 @@ class SumTree:
         leaf = idx_t - self.low_idx
         return (torch.div(leaf, self.B, rounding_mode="floor"), leaf % self.B), self.tree[idx_t]
 
-    def update_batch_priorities(self, priorities):
+    BATCH_KERNEL_MAX = 2048        # csrc/sumtree.cu kBatchMax: one CTA sorts the batch in shared memory
+
+    def update_batch_priorities(self, priorities, alpha=None):
         """sum_tree.py:130-138 + reconstruct :150-153.  ``priorities``: CUDA f32/f64 tensor (or numpy),
-        aligned with the last ``sample``; duplicates keep the first occurrence."""
-        pri = torch.as_tensor(priorities).to(self.device, dtype=torch.float64).reshape(-1)
+        aligned with the last ``sample``; duplicates keep the first occurrence.  With ``alpha`` the leaves become
+        ``priorities ** alpha`` evaluated as numpy's float32 power (prioritized.py:79) inside the same call.
+        Batches up to ``BATCH_KERNEL_MAX`` take the two-launch path (sort + pow + leaf write in one CTA, then the
+        ordered propagation); larger ones the generic sorted-segment path."""
         idx = self.prev_tree_idxs
+        n = idx.numel()
+        if n <= self.BATCH_KERNEL_MAX:
+            pri = torch.as_tensor(priorities)
+            if alpha is not None:
+                pri = pri.to(self.device, dtype=torch.float32).reshape(-1).contiguous()
+                p32, p64, a = _lib.ptr(pri), None, float(np.float32(alpha))
+            else:
+                pri = pri.to(self.device, dtype=torch.float64).reshape(-1).contiguous()
+                p32, p64, a = None, _lib.ptr(pri), 0.0
+            assert pri.numel() == n, "priorities must align with the last sample()"
+            if getattr(self, "_sorted_idx", None) is None or self._sorted_idx.numel() < n:
+                self._sorted_idx = torch.empty(max(n, 512), dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.call("rl_sumtree_update_batch", _lib.ptr(self.tree), self.tree_levels, _lib.ptr(idx.contiguous()),
+                          p32, a, p64, int(n), _lib.ptr(self._sorted_idx), _lib.ptr(self._scratch(n)), _lib.stream(),
+                          n_launch=2)
+            return
+        pri = torch.as_tensor(priorities)
+        if alpha is not None:
+            pri = _pow_alpha_f64(pri, alpha, self.device)
+        pri = pri.to(self.device, dtype=torch.float64).reshape(-1)
         if not self._sampled_unique:
             idx, perm = torch.sort(idx, stable=True)      # stable => first occurrence leads its run
             pri = pri[perm]

@@ -107,14 +107,18 @@ def test_sum_tree_known_answers_on_gpu(golden):
     assert idx.tolist() == [15, 16, 25, 26, 26]
 
 
+@pytest.mark.parametrize("batch_kernel", [True, False])
 @pytest.mark.parametrize("T,B,adv", [(3907, 256, 128), (64, 8, 50), (1000, 3, 17)])
-def test_sum_tree_random_stream_vs_oracle(T, B, adv):
+def test_sum_tree_random_stream_vs_oracle(T, B, adv, batch_kernel):
     """Config-4 scale (1 M leaves, 21 levels): advance / sample(512) / update loops against the numpy
-    oracle - whole tree bit-identical after every operation, sampled indices identical."""
+    oracle - whole tree bit-identical after every operation, sampled indices identical.  ``batch_kernel``: the
+    two-launch update (device sort in one CTA) or the generic sorted-segment path (torch.sort + set-leaves)."""
     from oracle.sum_tree import SumTree as Oracle
     from rlpyt_b200.replays.sum_tree import SumTree
     o = Oracle(T, B, off_backward=3, off_forward=3, default_value=1.0)
     d = SumTree(T, B, off_backward=3, off_forward=3, default_value=1.0)
+    if not batch_kernel:
+        d.BATCH_KERNEL_MAX = 0
     rng = np.random.default_rng(T)
     n_adv = 3 * T // adv + 3 if T < 2000 else 34
     for it in range(n_adv):
@@ -133,6 +137,29 @@ def test_sum_tree_random_stream_vs_oracle(T, B, adv):
         if it % 5 == 0 or it == n_adv - 1:
             assert np.array_equal(d.tree.cpu().numpy(), o.tree), it
     assert d.t == o.t
+
+
+@pytest.mark.parametrize("n", [1, 31, 512, 2048])
+def test_update_batch_with_folded_pow_equals_pow_then_update(n):
+    """``update_batch_priorities(p, alpha)`` (pow evaluated inside the batch kernel) leaves the tree bit-identical to
+    the separate pow kernel followed by the generic update - duplicates, unsorted indices and all batch sizes up to
+    the kernel's limit included."""
+    from rlpyt_b200.replays.sum_tree import SumTree, _pow_alpha_f64
+    trees = [SumTree(300, 7, off_backward=2, off_forward=2, default_value=1.0) for _ in range(2)]
+    trees[1].BATCH_KERNEL_MAX = 0
+    rng = np.random.default_rng(n)
+    for t in trees:
+        t.advance(250)
+    for rep in range(3):
+        u = rng.random(n)
+        pri = torch.from_numpy((np.abs(rng.standard_normal(n)) * 3 + 1e-4).astype(np.float32)).cuda()
+        for t in trees:
+            t.sample(n, random_values=u)
+        trees[0].update_batch_priorities(pri, alpha=0.6)
+        trees[1].update_batch_priorities(_pow_alpha_f64(pri, 0.6, pri.device))
+        assert torch.equal(trees[0].tree, trees[1].tree), rep
+        nodes = trees[0].tree.cpu().numpy()
+        np.testing.assert_allclose(nodes[0], nodes[trees[0].low_idx:trees[0].high_idx].sum(), rtol=1e-12)
 
 
 def test_pow_alpha_kernel_is_correctly_rounded_and_within_1ulp_of_numpy():
@@ -170,10 +197,14 @@ def test_replay_stream_device_pow_statistics(golden):
     np.testing.assert_allclose(ad.buf.priority_tree.tree.cpu().numpy(), g["mid_pri/final_tree"], rtol=1e-6, atol=1e-9)
 
 
-def test_extract_full_config_size():
+@pytest.mark.parametrize("vector", [False, True])
+def test_extract_full_config_size(vector, monkeypatch):
     """1M-frame-shaped extraction at batch 512 (84x84, 4 frames, n-step 3) on a smaller ring: frames
-    bit-identical to the oracle's gather, blanking included."""
+    bit-identical to the oracle's gather, blanking included - through the bulk-copy kernel (default) and the
+    vector-load fallback (csrc/replay.cu)."""
     from oracle.replay import FrameReplay
+    if vector:
+        monkeypatch.setenv("RLPYT_B200_REPLAY_VECTOR", "1")
     c = dict(obs_shape=(4, 84, 84), size=64 * 40, B=40, discount=0.99, n_step=3, prioritized=True, unique=False)
     ad = Adapter(c)
     o = FrameReplay(c["obs_shape"], c["size"], c["B"], discount=0.99, n_step_return=3)
