@@ -292,11 +292,11 @@ def run_replay(args):
                 "alpha .6 beta .4 (BASELINE.json configs[3])", {
         "dtype": "u8 frames, f64 sum-tree, int64 indices", "gpu_launches": launches, "clocks": clk.summary(),
         "config_l2": "replay store (7 GB) larger than L2; flushed between the per-phase timings",
-        "phases_us": {"sample_batch": t_sample * 1e6, "update_batch_priorities": t_update * 1e6, "replay_extract_kernel": t_ext * 1e6},
+        "phases_us": {"sample_batch": t_sample * 1e6, "update_batch_priorities": t_update * 1e6, "replay_extract_bulk_kernel": t_ext * 1e6},
         "e2e": {"value": 512 / t_host, "unit": "transitions/s", "us_per_step": t_host * 1e6,
                 "what": "sample_batch -> observations copied to pinned host memory; priorities uploaded from the host",
                 "h2d_bytes_per_step": 512 * 4, "d2h_bytes_per_step": 2 * 512 * 4 * 84 * 84},
-        "roofline": {"kernel": "replay_extract_kernel (512 samples x 2 x 4 frames)", "bound": "hbm", "achieved": nbytes / t_ext / 1e9,
+        "roofline": {"kernel": "replay_extract_bulk_kernel (512 samples x 2 stacks of 4 frames, cp.async.bulk)", "bound": "hbm", "achieved": nbytes / t_ext / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": nbytes / t_ext / 1e9 / peak, "traffic": None, "peak_source": how,
                      "us_per_launch": t_ext * 1e6, "algorithmic_bytes": nbytes},
         "cpu_baseline": {"value": 512 / (cpu_s + cpu_u), "unit": "transitions/s", "cores": 1, "kind": kind,
@@ -386,7 +386,7 @@ def run_dqn(args):
         "transitions_per_s": 512 / dt, "config_l2": "replay store (7 GB) larger than L2",
         "e2e": {"value": 1.0 / t_host, "unit": "updates/s", "what": "update + H2D of 4x256 new frames from pinned host memory + "
                 "D2H of the loss, wall clock", "h2d_bytes_per_step": int(host_obs.numel()), "d2h_bytes_per_step": 4},
-        "roofline": {"kernel": "replay_extract_kernel (512 samples x 2 x 4 frames)", "bound": "hbm", "achieved": nbytes / t_ext / 1e9,
+        "roofline": {"kernel": "replay_extract_bulk_kernel (512 samples x 2 stacks of 4 frames, cp.async.bulk)", "bound": "hbm", "achieved": nbytes / t_ext / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": nbytes / t_ext / 1e9 / peak, "traffic": None, "peak_source": how,
                      "us_per_launch": t_ext * 1e6, "algorithmic_bytes": nbytes,
                      "note": "the update itself is dominated by the Q-network (forward x3 + backward at batch 512)"},
