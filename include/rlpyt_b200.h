@@ -101,6 +101,14 @@ int rl_ppo_loss_f32(const float* prob_new, const float* value, const float* prob
                     const float* valid, int64_t N, int A, float ratio_clip,
                     float value_loss_coeff, float entropy_loss_coeff, float* out_scalars,
                     float* grad_prob, float* grad_value, void* scratch, void* stream);
+/* rl_ppo_loss_f32 with the ratio clip read from DEVICE memory (one float): the linear schedule of
+ * rlpyt/algos/pg/ppo.py:110-113 changes it every iteration, and a CUDA graph of the minibatch update captured once
+ * must follow it without being re-captured. */
+int rl_ppo_loss_devclip_f32(const float* prob_new, const float* value, const float* prob_old,
+                            const int64_t* action, const float* return_, const float* advantage,
+                            const float* valid, int64_t N, int A, const float* ratio_clip_dev,
+                            float value_loss_coeff, float entropy_loss_coeff, float* out_scalars,
+                            float* grad_prob, float* grad_value, void* scratch, void* stream);
 int rl_a2c_loss_f32(const float* prob, const float* value, const int64_t* action,
                     const float* return_, const float* advantage, const float* valid,
                     int64_t N, int A, float value_loss_coeff, float entropy_loss_coeff,

@@ -54,16 +54,17 @@ class FlatAdam(torch.optim.Optimizer):
 
     # ---- update ----------------------------------------------------------------------------
     @torch.no_grad()
-    def clip_and_step(self, max_norm=None):
+    def clip_and_step(self, max_norm=None, out=None):
         """[all-reduce ->] grad-norm -> clip -> Adam in two kernels.  Returns a 1-element CUDA
-        tensor holding the pre-clip gradient norm (no host sync)."""
+        tensor holding the pre-clip gradient norm (no host sync); ``out`` (1-element fp32 CUDA tensor) receives it
+        in place when given."""
         g = self.param_groups[0]
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad)  # SUM over ranks; the mean is folded into grad_scale
         self.step_count += 1
         self._opt_called = True  # what torch's lr_scheduler step-order check looks at
-        norm = torch.empty(1, dtype=torch.float32, device=self.flat_param.device)
+        norm = out if out is not None else torch.empty(1, dtype=torch.float32, device=self.flat_param.device)
         with torch.cuda.device(self.flat_param.device):
             _lib.call("rl_clip_adam_f32", _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad),
                       _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.numel, float(g["lr"]),

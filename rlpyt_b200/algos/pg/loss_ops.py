@@ -49,10 +49,17 @@ class _PpoLoss(torch.autograd.Function):
         gp = torch.empty_like(p) if need_grad else None
         gv = torch.empty_like(v) if need_grad else None
         with torch.cuda.device(p.device):
-            _lib.call("rl_ppo_loss_f32", _lib.ptr(p), _lib.ptr(v), _lib.ptr(po), _lib.ptr(a), _lib.ptr(R),
-                      _lib.ptr(A), _lib.ptr(m), N, n_act, float(ratio_clip), float(value_loss_coeff),
-                      float(entropy_loss_coeff), _lib.ptr(scalars), _lib.ptr(gp), _lib.ptr(gv),
-                      _lib.ptr(_scratch(N, p.device)), _lib.stream(), n_launch=2)
+            if isinstance(ratio_clip, torch.Tensor):      # device scalar: the value is read when the kernel RUNS (graph replays)
+                assert ratio_clip.is_cuda and ratio_clip.dtype == torch.float32 and ratio_clip.numel() == 1
+                _lib.call("rl_ppo_loss_devclip_f32", _lib.ptr(p), _lib.ptr(v), _lib.ptr(po), _lib.ptr(a), _lib.ptr(R),
+                          _lib.ptr(A), _lib.ptr(m), N, n_act, _lib.ptr(ratio_clip), float(value_loss_coeff),
+                          float(entropy_loss_coeff), _lib.ptr(scalars), _lib.ptr(gp), _lib.ptr(gv),
+                          _lib.ptr(_scratch(N, p.device)), _lib.stream(), n_launch=2)
+            else:
+                _lib.call("rl_ppo_loss_f32", _lib.ptr(p), _lib.ptr(v), _lib.ptr(po), _lib.ptr(a), _lib.ptr(R),
+                          _lib.ptr(A), _lib.ptr(m), N, n_act, float(ratio_clip), float(value_loss_coeff),
+                          float(entropy_loss_coeff), _lib.ptr(scalars), _lib.ptr(gp), _lib.ptr(gv),
+                          _lib.ptr(_scratch(N, p.device)), _lib.stream(), n_launch=2)
         if need_grad:
             ctx.save_for_backward(gp, gv)
         ctx.mark_non_differentiable(scalars)

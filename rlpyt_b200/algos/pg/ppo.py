@@ -84,42 +84,95 @@ class PPO(PolicyGradientAlgo):
             small.append(flat(valid))
         mb_size = batch_size // self.minibatches                       # ppo.py:90-91
         n_updates = self.epochs * (batch_size // mb_size)
-        stats = torch.zeros((n_updates, 4), dtype=torch.float32, device=dev)
+        stats = torch.zeros((n_updates, 9), dtype=torch.float32, device=dev)   # per update: the loss kernel's 8 scalars + gradNorm
         fused_opt = isinstance(self.optimizer, FlatAdam)
         lazy_obs = bool(getattr(self.agent.model, "accepts_lazy_rows", False)) and obs_f.dtype == torch.uint8
-        u = 0
-        for _ in range(self.epochs):                                   # ppo.py:92
-            for idxs in iterate_mb_idxs(batch_size, mb_size, shuffle=True):   # ppo.py:93
-                rows_np = (idxs % T) * B + (idxs // T)                 # ppo.py:94-95: [T_idxs, B_idxs]
-                rows = torch.from_numpy(rows_np).to(dev, non_blocking=True)
+        # every minibatch's rows of this iteration in one upload; the shuffles are drawn in the reference's order (ppo.py:92-95)
+        rows_np = np.stack([(idxs % T) * B + (idxs // T) for _ in range(self.epochs)
+                            for idxs in iterate_mb_idxs(batch_size, mb_size, shuffle=True)])
+        rows_all = torch.from_numpy(rows_np).to(dev, non_blocking=True)
+        mbg = self._minibatch_graph(obs_f, small, valid is not None, mb_size, lazy_obs) if (fused_opt and prof is None) else None
+        if mbg is not None:
+            mbg.clip.fill_(float(self.ratio_clip))
+        for u in range(n_updates):
+            if mbg is not None:
+                # gather -> forward -> fused loss -> backward into the flat gradient buffer: ONE graph launch
+                mbg.rows.copy_(rows_all[u], non_blocking=True)
+                mbg.graph.replay()
+                sc = mbg.sc
+            else:
+                rows = rows_all[u]
                 self.optimizer.zero_grad()                             # ppo.py:96
-                # models that read rows in place (fused first layer) get the un-gathered view
-                obs_mb = LazyRows(obs_f, rows) if lazy_obs else gather_rows(obs_f, rows)
-                got = gather_rows_multi(small, rows)
-                pa_mb, pr_mb, act_mb, ret_mb, adv_mb, oldp_mb = got[:6]
-                valid_mb = got[6] if valid is not None else None
-                dist_info, value = self.agent(obs_mb, pa_mb, pr_mb)    # ppo.py:133
-                ev()
-                loss, sc = loss_ops.ppo_loss(dist_info.prob, value, oldp_mb, act_mb, ret_mb, adv_mb, valid_mb,
-                                             self.ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
-                ev()
-                loss.backward()                                        # ppo.py:101
-                if fused_opt:
-                    grad_norm = self.optimizer.clip_and_step(self.clip_grad_norm)
-                else:
-                    grad_norm = torch.nn.utils.clip_grad_norm_(self.agent.parameters(), self.clip_grad_norm)
-                    self.optimizer.step()
-                stats[u, 0] = sc[0]
-                stats[u, 1] = grad_norm.reshape(())
-                stats[u, 2:4] = sc[1:3]
-                u += 1
-                self.update_counter += 1
+                sc = self._minibatch_forward_backward(obs_f, small, valid is not None, rows, lazy_obs, self.ratio_clip, ev)
+            if fused_opt:
+                self.optimizer.clip_and_step(self.clip_grad_norm, out=stats[u, 8:9])   # [all-reduce ->] clip + Adam
+            else:
+                stats[u, 8] = torch.nn.utils.clip_grad_norm_(self.agent.parameters(), self.clip_grad_norm).reshape(())
+                self.optimizer.step()
+            stats[u, :8].copy_(sc, non_blocking=True)
+            self.update_counter += 1
+        self._ff_iterations = getattr(self, "_ff_iterations", 0) + 1
         if self.linear_lr_schedule:                                    # ppo.py:110-113
             self.lr_scheduler.step()
             self.ratio_clip = self._ratio_clip * (self.n_itr - itr) / self.n_itr
-        host = stats[:u].cpu().numpy().astype(np.float64)              # the iteration's single D2H sync
-        return OptInfo(loss=host[:, 0].tolist(), gradNorm=host[:, 1].tolist(),
-                       entropy=host[:, 2].tolist(), perplexity=host[:, 3].tolist())
+        host = stats.cpu().numpy().astype(np.float64)                  # the iteration's single D2H sync
+        return OptInfo(loss=host[:, 0].tolist(), gradNorm=host[:, 8].tolist(),
+                       entropy=host[:, 1].tolist(), perplexity=host[:, 2].tolist())
+
+    def _minibatch_forward_backward(self, obs_f, small, has_valid, rows, lazy_obs, ratio_clip, ev=lambda: None):
+        """One minibatch of ppo.py:94-101 up to ``loss.backward()``: row gathers from the resident [T*B] buffers,
+        forward, fused loss (+ its gradient), backward into the flat gradient buffer.  Returns the loss kernel's
+        8 scalars (device)."""
+        # models that read rows in place (fused first layer) get the un-gathered view
+        obs_mb = LazyRows(obs_f, rows) if lazy_obs else gather_rows(obs_f, rows)
+        got = gather_rows_multi(small, rows)
+        pa_mb, pr_mb, act_mb, ret_mb, adv_mb, oldp_mb = got[:6]
+        valid_mb = got[6] if has_valid else None
+        dist_info, value = self.agent(obs_mb, pa_mb, pr_mb)            # ppo.py:133
+        ev()
+        loss, sc = loss_ops.ppo_loss(dist_info.prob, value, oldp_mb, act_mb, ret_mb, adv_mb, valid_mb,
+                                     ratio_clip, self.value_loss_coeff, self.entropy_loss_coeff)
+        ev()
+        loss.backward()                                                # ppo.py:101
+        return sc
+
+    MAX_MINIBATCH_GRAPHS = 2
+
+    def _minibatch_graph(self, obs_f, small, has_valid, mb_size, lazy_obs):
+        """The minibatch body above as ONE CUDA graph (ppo.py:94-101 is ~110 kernel launches of 3-250 us each; issued
+        from Python + autograd they leave the GPU idle for 10-15 % of the iteration).  The graph reads the sampler's
+        resident [T*B] buffers (fixed addresses: the sampler returns the same buffers every iteration), a static row
+        index vector and the ratio clip as a device scalar (it follows the linear schedule), and leaves the gradient in
+        the flat buffer; all-reduce and clip + Adam stay outside (their host scalars - learning rate, step count -
+        change per update).  Captured after one eager iteration (lazy initialisation must not happen under capture);
+        buffers at new addresses get a new graph, more than ``MAX_MINIBATCH_GRAPHS`` of them switch graphs off (a
+        caller that hands in fresh tensors every iteration would otherwise re-capture forever).
+        ``RLPYT_B200_LEARNER_GRAPH=0`` disables."""
+        import os
+        if os.environ.get("RLPYT_B200_LEARNER_GRAPH", "1") != "1" or getattr(self, "_ff_iterations", 0) < 1:
+            return None
+        graphs = self.__dict__.setdefault("_mb_graphs", {})
+        if graphs is None:
+            return None
+        key = (obs_f.data_ptr(), tuple(obs_f.shape), tuple((t.data_ptr(), tuple(t.shape)) for t in small), has_valid,
+               mb_size, lazy_obs, tuple(p.data_ptr() for p in self.agent.parameters()))
+        mbg = graphs.get(key)
+        if mbg is not None:
+            return mbg
+        if len(graphs) >= self.MAX_MINIBATCH_GRAPHS:
+            self._mb_graphs = None                                     # thrashing: stay eager from now on
+            return None
+        from types import SimpleNamespace
+        dev = obs_f.device
+        mbg = SimpleNamespace(rows=torch.zeros(mb_size, dtype=torch.int64, device=dev),
+                              clip=torch.full((1,), float(self.ratio_clip), dtype=torch.float32, device=dev),
+                              graph=torch.cuda.CUDAGraph(), keep=(obs_f, small))
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(mbg.graph):
+            self.optimizer.zero_grad()
+            mbg.sc = self._minibatch_forward_backward(obs_f, small, has_valid, mbg.rows, lazy_obs, mbg.clip)
+        graphs[key] = mbg
+        return mbg
 
     def _optimize_recurrent(self, itr, samples):
         """The recurrent branch of ppo.py:59-115 (:84-86 ``init_rnn_state = prev_rnn_state[0]`` kept ``[B,N,H]`` for

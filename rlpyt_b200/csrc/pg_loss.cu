@@ -37,8 +37,9 @@ pg_loss_kernel(const float* __restrict__ prob_new, const float* __restrict__ val
                const float* __restrict__ ret, const float* __restrict__ adv,
                const float* __restrict__ valid, int64_t N, int A, float clip, float c_v, float c_ent,
                float* __restrict__ grad_prob, float* __restrict__ grad_value,
-               double* __restrict__ partials) {
+               double* __restrict__ partials, const float* __restrict__ clip_dev) {
     __shared__ double sh[kLossSums][kLossThreads / 32];
+    if (PPO && clip_dev != nullptr) clip = *clip_dev;      // ratio clip as a device scalar: a captured CUDA graph follows the schedule
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kLossThreads + threadIdx.x;
     double acc[kLossSums] = {0, 0, 0, 0, 0};
     if (i < N) {
@@ -148,11 +149,12 @@ template <bool PPO>
 static int launch_loss(const float* prob_new, const float* value, const float* prob_old,
                        const int64_t* action, const float* ret, const float* adv, const float* valid,
                        int64_t N, int A, float clip, float c_v, float c_ent, float* scalars,
-                       float* grad_prob, float* grad_value, void* scratch, cudaStream_t st) {
+                       float* grad_prob, float* grad_value, void* scratch, cudaStream_t st,
+                       const float* clip_dev = nullptr) {
     const int nb = loss_blocks(N);
     double* partials = static_cast<double*>(scratch);
     pg_loss_kernel<PPO><<<nb, kLossThreads, 0, st>>>(prob_new, value, prob_old, action, ret, adv, valid,
-                                                     N, A, clip, c_v, c_ent, grad_prob, grad_value, partials);
+                                                     N, A, clip, c_v, c_ent, grad_prob, grad_value, partials, clip_dev);
     int rc = check_launch("pg_loss_kernel");
     if (rc != RL_OK) return rc;
     const int masked = valid != nullptr;
@@ -183,6 +185,20 @@ int rl_ppo_loss_f32(const float* prob_new, const float* value, const float* prob
     return rl::launch_loss<true>(prob_new, value, prob_old, action, return_, advantage, valid, N, A,
                                  ratio_clip, value_loss_coeff, entropy_loss_coeff, out_scalars,
                                  grad_prob, grad_value, scratch, rl::as_stream(stream));
+}
+
+int rl_ppo_loss_devclip_f32(const float* prob_new, const float* value, const float* prob_old,
+                            const int64_t* action, const float* return_, const float* advantage,
+                            const float* valid, int64_t N, int A, const float* ratio_clip_dev, float value_loss_coeff,
+                            float entropy_loss_coeff, float* out_scalars, float* grad_prob, float* grad_value,
+                            void* scratch, void* stream) {
+    RL_REQUIRE(prob_new && value && prob_old && action && return_ && advantage && out_scalars && scratch && ratio_clip_dev,
+               RL_EINVAL, "rl_ppo_loss_devclip_f32: null pointer");
+    RL_REQUIRE(N >= 1 && A >= 1 && A <= rl::kMaxA, RL_EINVAL, "rl_ppo_loss_devclip_f32: N=%lld A=%d", (long long)N, A);
+    RL_REQUIRE(rl::aligned(scratch, 8), RL_EALIGN, "rl_ppo_loss_devclip_f32: scratch must be 8B aligned");
+    return rl::launch_loss<true>(prob_new, value, prob_old, action, return_, advantage, valid, N, A, 0.0f,
+                                 value_loss_coeff, entropy_loss_coeff, out_scalars, grad_prob, grad_value, scratch,
+                                 rl::as_stream(stream), ratio_clip_dev);
 }
 
 int rl_a2c_loss_f32(const float* prob, const float* value, const int64_t* action, const float* return_,

@@ -69,6 +69,8 @@ class AsyncSamplerMixin:
         super().initialize(twin, affinity=affinity, seed=self.seed, bootstrap_value=self._bootstrap_value)
         self.master_agent = master
         self.agent = twin
+        for ro in ([self.rollout] if hasattr(self, "rollout") else []) + list(getattr(self, "rollouts", [])):
+            ro.capture_error_mode = "thread_local"           # the optimizer thread keeps issuing CUDA calls while a step graph is captured
 
     def obtain_samples(self, itr, db_idx):
         """async_/serial_sampler.py:79-91 / async_/base.py:62-74: take new parameters if the optimizer published any,

@@ -34,6 +34,7 @@ class DeviceRollout:
         # lazily after an eager warm-up batch (cuDNN autotuning cannot run under capture).
         self.use_graphs = os.environ.get("RLPYT_B200_SAMPLER_GRAPHS", "1") == "1"
         self._warned_unpinned = False
+        self.capture_error_mode = "global"
         self._graphs = {}
         self._eager_batches = 0
 
@@ -122,7 +123,9 @@ class DeviceRollout:
         if g is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(g, stream=self.side_stream):
+            # "thread_local": in the asynchronous runner other threads of this process keep issuing CUDA calls
+            # (synchronisations, allocations) on their own streams while this thread captures
+            with torch.cuda.graph(g, stream=self.side_stream, capture_error_mode=self.capture_error_mode):
                 body()
             self._graphs[key] = g
         g.replay()

@@ -286,3 +286,60 @@ def test_model_tensor_core_head_matches_cublas_head():
     for a, b in zip(g1, g2):
         s = float(b.abs().max()) + 1e-12
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=2e-5 * s)
+
+
+@pytest.mark.parametrize("normalize,image", [(False, (4, 84, 84)), (True, (4, 36, 36))])
+def test_minibatch_cuda_graph_is_bit_identical_to_eager_issue(normalize, image, monkeypatch):
+    """PPO.optimize_agent replays the minibatch body (gather -> forward -> fused loss -> backward) as ONE CUDA graph from
+    the second iteration on (algos/pg/ppo.py ``_minibatch_graph``).  Same kernels, same order, same inputs: four
+    iterations over a sample buffer that is rewritten IN PLACE between iterations (what the samplers do) must leave
+    parameters, Adam state and OptInfo bit-identical to the eagerly issued run - including the linearly scheduled
+    learning rate and ratio clip (the clip reaches the captured loss kernel through a device scalar)."""
+    from oracle import atari_ff
+    from rlpyt_b200.agents.pg.atari import AtariFfAgent
+    from rlpyt_b200.agents.pg.base import AgentInfo
+    from rlpyt_b200.algos.pg.ppo import PPO
+    from rlpyt_b200.distributions.categorical import DistInfo
+    from rlpyt_b200.samplers.collections import AgentSamplesBsv, BatchSpec, EnvSamples, Samples
+    Tn, Bn, An = 16, 32, 6
+    sd0 = atari_ff.init_state_dict(image, An, seed=7)
+
+    def run(graph):
+        monkeypatch.setenv("RLPYT_B200_LEARNER_GRAPH", "1" if graph else "0")
+        agent = AtariFfAgent(initial_model_state_dict={k: v.clone() for k, v in sd0.items()})
+        agent.initialize(Spaces(Obs(image), Act(An)))
+        agent.to_device(0)
+        algo = PPO(gae_lambda=0.95, minibatches=4, epochs=2, normalize_advantage=normalize, ratio_clip=0.2)
+        algo.initialize(agent, 10, BatchSpec(Tn, Bn), mid_batch_reset=not normalize)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        all_a = torch.zeros(Tn + 1, Bn, dtype=torch.int64, device="cuda")
+        all_r = torch.zeros(Tn + 1, Bn, device="cuda")
+        samples = Samples(
+            agent=AgentSamplesBsv(action=all_a[1:], prev_action=all_a[:-1],
+                                  agent_info=AgentInfo(dist_info=DistInfo(prob=torch.zeros(Tn, Bn, An, device="cuda")),
+                                                       value=torch.zeros(Tn, Bn, device="cuda")),
+                                  bootstrap_value=torch.zeros(1, Bn, device="cuda")),
+            env=EnvSamples(observation=torch.zeros((Tn, Bn) + image, dtype=torch.uint8, device="cuda"), reward=all_r[1:],
+                           prev_reward=all_r[:-1], done=torch.zeros(Tn, Bn, dtype=torch.bool, device="cuda"), env_info=None))
+        infos = []
+        np.random.seed(9)
+        agent.train_mode(0)
+        for itr in range(4):
+            samples.env.observation.copy_(torch.randint(0, 256, samples.env.observation.shape, dtype=torch.uint8, device="cuda", generator=g))
+            all_a.copy_(torch.randint(0, An, all_a.shape, device="cuda", generator=g))
+            all_r.copy_(torch.randn(all_r.shape, device="cuda", generator=g))
+            samples.env.done.copy_(torch.rand(Tn, Bn, device="cuda", generator=g) < 0.05)
+            samples.agent.agent_info.value.copy_(torch.randn(Tn, Bn, device="cuda", generator=g))
+            samples.agent.agent_info.dist_info.prob.copy_(torch.softmax(torch.randn(Tn, Bn, An, device="cuda", generator=g), -1))
+            samples.agent.bootstrap_value.copy_(torch.randn(1, Bn, device="cuda", generator=g))
+            infos.append(algo.optimize_agent(itr, samples))
+        n_graphs = len(algo.__dict__.get("_mb_graphs") or {})
+        return algo.optimizer.flat_param.clone(), algo.optimizer.exp_avg_sq.clone(), infos, n_graphs
+
+    p_e, v_e, i_e, g_e = run(False)
+    p_g, v_g, i_g, g_g = run(True)
+    assert g_e == 0 and g_g == 1                                   # one capture served iterations 1..3
+    assert torch.equal(p_e, p_g) and torch.equal(v_e, v_g)
+    for a, b in zip(i_e, i_g):
+        for f in ("loss", "gradNorm", "entropy", "perplexity"):
+            assert getattr(a, f) == getattr(b, f), f
