@@ -217,7 +217,9 @@ def run_b200(args):
         sampler_profile = None
         pr = getattr(sampler, "profile", None)
         if pr and pr.get("steps"):   # RLPYT_B200_SAMPLER_PROFILE=1: master-side split of one env step
-            sampler_profile = {k[:-2]: pr[k] / pr["steps"] * 1e6 for k in ("wait_envs_s", "device_step_s", "release_s")}
+            sampler_profile = {k[:-2]: pr[k] / pr["steps"] * 1e6 for k in pr if k.endswith("_s")}
+            if "early_uploads" in pr:
+                sampler_profile["early_upload_frac"] = pr["early_uploads"] / (2 * pr["steps"])
         params_identical = None
         if world > 1:   # data-parallel replicas must hold bit-identical parameters after K+W updates x 16
             flat = algo.optimizer.flat_param if hasattr(algo.optimizer, "flat_param") else torch.cat(

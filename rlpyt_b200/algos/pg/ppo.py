@@ -14,6 +14,7 @@ Recurrent agents (ppo.py:84-100, 127-131) train on whole trajectories, minibatch
 import numpy as np
 import torch
 
+from rlpyt_b200 import _lib
 from rlpyt_b200.agents.base import AgentInputs
 from rlpyt_b200.algos.optim import FlatAdam
 from rlpyt_b200.algos.pg import loss_ops
@@ -99,6 +100,7 @@ class PPO(PolicyGradientAlgo):
                 # gather -> forward -> fused loss -> backward into the flat gradient buffer: ONE graph launch
                 mbg.rows.copy_(rows_all[u], non_blocking=True)
                 mbg.graph.replay()
+                _lib.launch_count += mbg.n_launch                      # this package's kernels inside the graph (bench.py's count)
                 sc = mbg.sc
             else:
                 rows = rows_all[u]
@@ -168,9 +170,11 @@ class PPO(PolicyGradientAlgo):
                               clip=torch.full((1,), float(self.ratio_clip), dtype=torch.float32, device=dev),
                               graph=torch.cuda.CUDAGraph(), keep=(obs_f, small))
         torch.cuda.synchronize(dev)
+        n0 = _lib.launch_count
         with torch.cuda.graph(mbg.graph):
             self.optimizer.zero_grad()
             mbg.sc = self._minibatch_forward_backward(obs_f, small, has_valid, mbg.rows, lazy_obs, mbg.clip)
+        mbg.n_launch, _lib.launch_count = _lib.launch_count - n0, n0   # capturing launched nothing
         graphs[key] = mbg
         return mbg
 

@@ -114,10 +114,12 @@ class AlternatingSampler(GpuSampler):
                 uploaded[alt] = False
                 t1 = clock() if prof is not None else 0.0
                 ro.act_async(t, blank_done_rows=wait_reset)
+                ta = clock() if prof is not None else 0.0
                 other, t_other = alt ^ 1, (t if alt == 0 else t + 1)
                 if t_other < T and take_observations(other, False):
                     start_upload(other, t_other)             # overlaps this half's agent.step
                     uploaded[other] = True
+                tb = clock() if prof is not None else 0.0
                 ro.wait()                                    # actions of this half are in the step buffer
                 t2 = clock() if prof is not None else 0.0
                 for s in self.act_ready_pair[alt]:
@@ -126,6 +128,10 @@ class AlternatingSampler(GpuSampler):
                     prof["wait_envs_s"] += t1 - t0
                     prof["device_step_s"] += t2 - t1
                     prof["release_s"] += clock() - t2
+                    prof["act_launch_s"] = prof.get("act_launch_s", 0.0) + (ta - t1)
+                    prof["other_upload_s"] = prof.get("other_upload_s", 0.0) + (tb - ta)
+                    prof["stream_wait_s"] = prof.get("stream_wait_s", 0.0) + (t2 - tb)
+                    prof["early_uploads"] = prof.get("early_uploads", 0) + (1 if uploaded[other] else 0)
                     prof["steps"] += 0.5                     # two half steps = one env step of the whole batch
         for alt in range(2):
             ro, sl = self.rollouts[alt], self.halves[alt]
