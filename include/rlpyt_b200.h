@@ -45,6 +45,11 @@ int rl_b200_sm_count(void);
  * Host pointers; no CUDA call inside; safe in forked worker processes. */
 int rl_host_stream_copy(void* dst, const void* src, int64_t nbytes);
 
+/* Host (page-locked) -> device copy of one env worker's observation rows, stream-ordered (cudaMemcpyAsync): the
+ * master half of rlpyt/samplers/parallel/gpu/action_server.py:46-48, issued per worker as each one signals
+ * obs_ready instead of once for the whole step buffer. */
+int rl_upload_async(void* dst_device, const void* src_host, int64_t nbytes, void* stream);
+
 /* ------------------------------------------------------------------ returns (K1-K4)
  * algo: 0 = auto, 1 = streaming column kernel (thread per 1/4 columns, sequential in t,
  *       reference operation order => bit-identical to the reference),

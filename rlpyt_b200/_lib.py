@@ -22,6 +22,7 @@ SIGNATURES = {
     "rl_b200_last_error": (c_char_p, []),
     "rl_b200_sm_count": (c_int, []),
     "rl_host_stream_copy": (c_int, [P, P, c_int64]),
+    "rl_upload_async": (c_int, [P, P, c_int64, P]),
     "rl_gae_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_float, c_int, P]),
     "rl_discount_return_f32": (c_int, [P, P, P, P, P, P, c_int, c_int64, c_float, c_int, P]),
     "rl_nstep_return_f32": (c_int, [P, P, P, P, P, c_int, c_int64, c_int, c_int, P]),

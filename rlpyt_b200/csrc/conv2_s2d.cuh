@@ -549,7 +549,12 @@ inline cudaError_t launch_dgrad(const float* G, const float* W, float* dX, const
 // accumulator lives in lanes 0-15 / 32-47 / 64-79 / 96-111, tcgen05_shift_probe).  The tensor-core accumulator
 // truncates, so every image's partial (K = 128 cells) is promoted into fp32 registers by eight accumulator warps
 // (two TMEM buffers: the drain of image i overlaps the MMAs of image i+1); per-CTA partial sums are reduced over
-// CTAs in a fixed order (deterministic).  3-term TF32 split, 192 MMAs (M=64, N=32, K=8) per image.
+// CTAs in a fixed order (deterministic).  3-term TF32 split.
+// The two bx taps of a by row share ONE MMA: sum_r A[r+s+1] G[r] = sum_r' A[r'+s] G[r'-1], so with the gradient rows
+// staged 4 rows down (rows 0-3 of the plane stay zero) the B operand is N = 64 = two overlapping 32-column atoms,
+// atom 0 = the plane from row 3 (G[r'-1]: bx = 1), atom 1 = LBO = 128 bytes further (G[r']: bx = 0).  96 MMAs
+// (M=64, N=64, K=8) per image instead of 192 with N=32 - the kernel was bound by the tensor pipe's per-instruction
+// cost at small N (ncu: pipe 65 % busy at 240 us).
 namespace wg2 {
 
 constexpr int kThreadsW = 576;                 // warps 0-7 re-layout, 8-15 accumulators, 16 MMA + TMEM, 17 loader
@@ -611,8 +616,9 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-    // A and B MN-major (bits 15, 16), M = 64, N = 32
-    constexpr uint32_t kIdesc = make_idesc_tf32(64, kOC) | (1u << 15) | (1u << 16);
+    // A and B MN-major (bits 15, 16), M = 64, N = 64 (two bx taps x 32 oc)
+    constexpr uint32_t kIdesc = make_idesc_tf32(64, 2 * kOC) | (1u << 15) | (1u << 16);
+    constexpr int kGRow0 = 4;                        // gradient row r is staged at plane row r + 4; rows 0-3 stay zero
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRaw; ++s) {
@@ -656,6 +662,11 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
         // ================================================================ re-layout (the forward's cell rows + the dgrad's gradient rows)
         const int q_end = kRows + g.GW + 1;
         float bias_acc[4] = {0.f, 0.f, 0.f, 0.f};            // channels 4*warp .. 4*warp+3, this lane's rows
+        if (warp == 0) {                                     // the zero rows in front of the gradient planes (hi, lo), once
+            const uint32_t z[4] = {0u, 0u, 0u, 0u};
+            sts128u(gt_u32 + static_cast<uint32_t>(lane) * 16u, z);
+            sts128u(gt_u32 + kGPlane + static_cast<uint32_t>(lane) * 16u, z);
+        }
         uint32_t it = 0;
         for (int i = 0; i < n_local; ++i) {
             const int s = i % kRaw;
@@ -702,7 +713,10 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
                             const uint32_t hi = a_u32 + static_cast<uint32_t>(plane * 2 * kPlaneBytes) + off;
                             split_store(hi, hi + kPlaneBytes, va[plane][u]);
                         }
-                        if (q < kRows) split_store(gt_u32 + off, gt_u32 + kGPlane + off, vg[u]);
+                        if (q < kRows) {
+                            const uint32_t goff = mn32_chunk_off(q + kGRow0, warp);
+                            split_store(gt_u32 + goff, gt_u32 + kGPlane + goff, vg[u]);
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -730,12 +744,14 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
                     const uint8_t* a_hi = smem + L.a_off;            // plane 0 hi; plane 1 hi is 2*kPlaneBytes further (= LBO)
                     const uint8_t* g_hi = smem + L.g_off;
 #pragma unroll
-                    for (int tap = 0; tap < 4; ++tap) {
-                        const int shift = (tap >> 1) * g.GW + (tap & 1);
-                        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 4 * kOC + tap * kOC);
+                    for (int by = 0; by < 2; ++by) {
+                        const int shift = by * g.GW;                  // bx rides on the B operand's two atoms
+                        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * 4 * kOC + by * 2 * kOC);
                         const uint64_t dah = make_desc_mn(a_hi + shift * 128, 2 * kPlaneBytes);
                         const uint64_t dal = make_desc_mn(a_hi + kPlaneBytes + shift * 128, 2 * kPlaneBytes);
-                        const uint64_t dgh = make_desc_mn(g_hi, 1024), dgl = make_desc_mn(g_hi + kGPlane, 1024);
+                        // atom 0 = rows from kGRow0 - 1 (G[r-1] -> bx = 1), atom 1 = 128 bytes further (G[r] -> bx = 0)
+                        const uint64_t dgh = make_desc_mn(g_hi + (kGRow0 - 1) * 128, 128);
+                        const uint64_t dgl = make_desc_mn(g_hi + kGPlane + (kGRow0 - 1) * 128, 128);
 #pragma unroll 4
                         for (int k = 0; k < 16; ++k) {                // K = 8 cells per MMA: one 1024-byte atom of rows
                             const uint64_t adv = static_cast<uint64_t>(64 * k);
@@ -783,7 +799,8 @@ conv2_s2d_wgrad_kernel(const float* __restrict__ X, const float* __restrict__ G,
             const int m = 16 * quarter + lane;
 #pragma unroll
             for (int tp = 0; tp < 2; ++tp) {
-                float4* dst = reinterpret_cast<float4*>(partial + ((static_cast<int64_t>(blockIdx.x) * 4 + 2 * half + tp) * 64 + m) * kOC);
+                // column block 2*half + tp of the accumulators = tap (by = half, bx = 1 - tp): atom 0 of B is the bx = 1 tap
+                float4* dst = reinterpret_cast<float4*>(partial + ((static_cast<int64_t>(blockIdx.x) * 4 + 2 * half + (1 - tp)) * 64 + m) * kOC);
 #pragma unroll
                 for (int j = 0; j < kOC / 4; ++j)
                     dst[j] = make_float4(acc[tp][4 * j], acc[tp][4 * j + 1], acc[tp][4 * j + 2], acc[tp][4 * j + 3]);

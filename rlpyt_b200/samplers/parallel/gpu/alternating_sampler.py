@@ -70,6 +70,8 @@ class AlternatingSampler(GpuSampler):
                           pinned=host.get("pinned", False))
             ro = DeviceRollout(self.samples[:, sl], host_h, self.agent, self.device, stream=torch.cuda.Stream(self.device))
             ro.in_action.copy_(host_h["step_pyt"].action)
+            w0 = 0 if sl.start == 0 else half_w
+            ro.set_worker_chunks([slice(ws.start - sl.start, ws.stop - sl.start) for ws in self.worker_slices[w0:w0 + half_w]])
             self.rollouts.append(ro)
 
     def serve_actions(self, itr):
@@ -84,41 +86,56 @@ class AlternatingSampler(GpuSampler):
             current = torch.cuda.current_stream(self.device)
             for ro in self.rollouts:
                 ro.side_stream.wait_stream(current)          # the learner's last update is ordered before this batch
-        got = [set(), set()]                                 # obs_ready handshakes already taken for each half's next event
+        # Each half's observations are uploaded PER WORKER, as soon as that worker has signalled (rl_upload_async): the
+        # master polls the other half's workers while it waits for this half's agent.step, so by the time the last worker
+        # of a half is done the rows of the others are already in HBM.  (Measured on the B200 host, profiles/
+        # r02_sampler_halfstep.json: H2D of a half 100 us + agent.step 94 us were strictly serial per half, because the
+        # other half's workers were never done yet when the master looked once right after launching agent.step.)
+        pending = [list(range(len(p))) for p in self.obs_ready_pair]   # workers whose obs_ready for the half's next event is still to be taken
         uploaded = [False, False]
+        half_w = len(self.obs_ready_pair[0])
 
-        def take_observations(alt, block):
-            for i, sem in enumerate(self.obs_ready_pair[alt]):
-                if i not in got[alt]:
-                    if not sem.acquire(block=block):
-                        return False
-                    got[alt].add(i)
-            got[alt].clear()
-            return True
+        def poll(alt, k, block):
+            """Take the obs_ready handshakes that are available (all of them when ``block``), uploading each worker's rows at once."""
+            ro, sems, left = self.rollouts[alt], self.obs_ready_pair[alt], pending[alt]
+            i = 0
+            while i < len(left):
+                w = left[i]
+                if sems[w].acquire(block=block):
+                    ro.upload_worker_rows(k, w)
+                    left.pop(i)
+                else:
+                    i += 1
+            return not left
 
-        def start_upload(alt, t):
+        def finish_upload(alt, k):
             ro, sl = self.rollouts[alt], self.halves[alt]
+            pending[alt] = list(range(half_w))
             done_now = ro.step_np.done
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=int(b) + sl.start)
-            ro.upload_async(t, zero_inputs_on_done=True)
+            ro.upload_async(k, zero_inputs_on_done=True, obs_done=True)     # reward / done / agent inputs
 
         for t in range(T):
             for alt in range(2):
                 ro = self.rollouts[alt]
                 t0 = clock() if prof is not None else 0.0
                 if not uploaded[alt]:
-                    take_observations(alt, True)             # this half wrote obs(t), reward(t-1), done(t-1)
-                    start_upload(alt, t)
+                    poll(alt, t, True)                       # this half wrote obs(t), reward(t-1), done(t-1)
+                    finish_upload(alt, t)
                 uploaded[alt] = False
                 t1 = clock() if prof is not None else 0.0
                 ro.act_async(t, blank_done_rows=wait_reset)
                 ta = clock() if prof is not None else 0.0
                 other, t_other = alt ^ 1, (t if alt == 0 else t + 1)
-                if t_other < T and take_observations(other, False):
-                    start_upload(other, t_other)             # overlaps this half's agent.step
-                    uploaded[other] = True
+                if t_other < T:
+                    while not uploaded[other]:               # serve the other half's workers while this half's step runs
+                        if poll(other, t_other, False):
+                            finish_upload(other, t_other)
+                            uploaded[other] = True
+                        elif ro.act_done():
+                            break
                 tb = clock() if prof is not None else 0.0
                 ro.wait()                                    # actions of this half are in the step buffer
                 t2 = clock() if prof is not None else 0.0

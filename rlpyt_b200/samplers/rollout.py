@@ -35,6 +35,7 @@ class DeviceRollout:
         self.use_graphs = os.environ.get("RLPYT_B200_SAMPLER_GRAPHS", "1") == "1"
         self._warned_unpinned = False
         self.capture_error_mode = "global"
+        self._act_event = None
         self._graphs = {}
         self._eager_batches = 0
 
@@ -43,10 +44,30 @@ class DeviceRollout:
         """Where observation(k) lives in HBM: row k of the batch, or the bootstrap slot for k == T."""
         return self.samples.env.observation[k] if k < self.T else self.obs_extra
 
-    def upload_obs_chunk(self, obs_dst, sl):
-        """Async H2D of one worker's rows as soon as that worker is done (its DMA overlaps the
-        workers still stepping)."""
-        obs_dst[sl].copy_(self.step_pyt.observation[sl], non_blocking=True)
+    def set_worker_chunks(self, slices):
+        """``slices``: each env worker's rows of THIS engine's B range.  Enables ``upload_worker_rows``: the observation
+        rows of one worker go to HBM as soon as that worker has signalled (one thin cudaMemcpyAsync through the C ABI),
+        so the H2D of a step overlaps the workers that are still stepping and only the last worker's rows are on the
+        critical path; ``upload_async(k, ..., obs_done=True)`` then moves the small fields only."""
+        from rlpyt_b200 import _lib
+        obs = self.step_np.observation
+        self._row_bytes = int(obs[0].nbytes)
+        self._chunks = [(int(sl.start), int(sl.stop - sl.start)) for sl in slices]
+        self._src_base = int(obs.ctypes.data)
+        self._upload_fn = _lib.load().rl_upload_async
+        self._dst_base = {}
+
+    def upload_worker_rows(self, k, i):
+        start, n = self._chunks[i]
+        base = self._dst_base.get(k)
+        if base is None:
+            base = self._dst_base[k] = int(self.obs_slot(k).data_ptr())
+        off = start * self._row_bytes
+        stream = self.side_stream if self.side_stream is not None else torch.cuda.current_stream(self.device)
+        rc = self._upload_fn(base + off, self._src_base + off, n * self._row_bytes, stream.cuda_stream)
+        if rc != 0:
+            from rlpyt_b200 import _lib
+            _lib.check(rc, "rl_upload_async")
 
     def upload(self, k, zero_inputs_on_done, obs_done=False):
         """Event k (0..T): the envs have written observation(k), reward(k-1), done(k-1) into the
@@ -132,15 +153,23 @@ class DeviceRollout:
 
     # ---- the same step in two launches (alternating sampler): upload_async(k) may be issued while the OTHER half's
     # act is still running on its own stream; act_async(k) follows on this half's stream; wait() = actions on the host
-    def upload_async(self, k, zero_inputs_on_done):
+    def upload_async(self, k, zero_inputs_on_done, obs_done=False):
         def body():
-            self.upload(k, zero_inputs_on_done)
+            self.upload(k, zero_inputs_on_done, obs_done=obs_done)
             if k == 0:
                 self.begin_batch()
-        self._run(("up", k, zero_inputs_on_done), body)
+        self._run(("up", k, zero_inputs_on_done, obs_done), body)
 
     def act_async(self, k, blank_done_rows=False):
         self._run(("act", k, blank_done_rows), lambda: self.act(k, self.obs_slot(k), blank_done_rows=blank_done_rows, sync=False))
+        if self.side_stream is not None:
+            if self._act_event is None:
+                self._act_event = torch.cuda.Event()
+            self._act_event.record(self.side_stream)
+
+    def act_done(self):
+        """Non-blocking: have the actions of the last ``act_async`` reached the step buffer?"""
+        return self._act_event is None or self._act_event.query()
 
     def wait(self):
         (self.side_stream or torch.cuda.current_stream(self.device)).synchronize()

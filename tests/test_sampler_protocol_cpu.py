@@ -112,23 +112,40 @@ def test_worker_protocol_against_host_replay(kind):
 
 class _FakeRollout:
     """Stands in for DeviceRollout on the CPU: 'agent.step' = seeded random actions written to the step buffer;
-    records the order of events so the alternating master loop can be checked."""
+    records the order of events so the alternating master loop can be checked.  ``upload_worker_rows`` snapshots a
+    worker's rows of the step buffer at the moment the master issues their DMA (it does so per worker, as soon as that
+    worker has signalled - possibly while the OTHER half's agent.step is in flight): the rows must already be the
+    observations of step k."""
 
-    def __init__(self, step_np, rng, log, tag):
+    def __init__(self, step_np, rng, log, tag, chunks):
         self.step_np, self.rng, self.log, self.tag = step_np, rng, log, tag
+        self.chunks = chunks                              # (start, n) of each worker within this half
         self.obs_seen = []
+        self._cur = {}
+        self._polls = 0
 
     side_stream = None
 
-    def upload_async(self, t, zero_inputs_on_done):
-        """What the real engine DMAs at this moment: the master may call this for the other half while one half's
-        agent.step is in flight - the observations must already be the ones of step t."""
-        self.obs_seen.append(self.step_np.observation.copy())
+    def upload_worker_rows(self, k, i):
+        start, n = self.chunks[i]
+        buf = self._cur.setdefault(k, np.zeros_like(self.step_np.observation))
+        buf[start:start + n] = self.step_np.observation[start:start + n]
+        self.log.append((self.tag, "rows", k, i))
+
+    def upload_async(self, t, zero_inputs_on_done, obs_done=False):
+        assert obs_done, "the alternating master uploads observations per worker"
+        assert sorted(e[3] for e in self.log if e[:3] == (self.tag, "rows", t)) == list(range(len(self.chunks)))
+        self.obs_seen.append(self._cur.pop(t))
         self.log.append((self.tag, "up", t))
 
     def act_async(self, t, blank_done_rows=False):
         self.step_np.action[:] = self.rng.integers(0, A, len(self.step_np.action))
         self.log.append((self.tag, t))
+        self._polls = 0
+
+    def act_done(self):
+        self._polls += 1                                  # the 'device' takes a few polls: the master keeps serving the other half
+        return self._polls > 3
 
     def wait(self):
         pass
@@ -185,7 +202,8 @@ def test_alternating_master_loop_against_real_workers(kind):
     s.obs_ready_pair = (obs_ready[:half_w], obs_ready[half_w:])
     s.act_ready_pair = (act_ready[:half_w], act_ready[half_w:])
     log = []
-    s.rollouts = [_FakeRollout(step[sl], np.random.default_rng(i), log, i) for i, sl in enumerate(s.halves)]
+    s.rollouts = [_FakeRollout(step[sl], np.random.default_rng(i), log, i, [(w * n_envs, n_envs) for w in range(half_w)])
+                  for i, sl in enumerate(s.halves)]
     # host replay
     replay_envs = []
     for w in range(n_worker):
