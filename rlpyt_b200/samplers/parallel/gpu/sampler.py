@@ -176,6 +176,7 @@ class GpuSampler(BaseSampler):
                     w.terminate()
             raise RuntimeError(f"sampler workers did not come up (dead: {dead})") from e
         self.rollout = DeviceRollout(self.samples, self.host, agent, self.device)
+        self.rollout.set_worker_chunks(self.worker_slices)
         self.profile = dict(wait_envs_s=0.0, device_step_s=0.0, release_s=0.0, steps=0)
         self.rollout.in_action.copy_(self.host["step_pyt"].action)
         self.samples_pyt = self.samples
@@ -229,16 +230,29 @@ class GpuSampler(BaseSampler):
         wait_reset = not self.mid_batch_reset
         prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
         clock = time.perf_counter
+        n_worker = len(obs_ready)
         for t in range(T):
             t0 = clock() if prof is not None else 0.0
-            for s in obs_ready:
-                s.acquire()  # workers wrote obs(t), reward(t-1), done(t-1)
+            # workers wrote obs(t), reward(t-1), done(t-1): each worker's rows go to HBM as soon as it has signalled,
+            # overlapping the H2D with the workers that are still stepping (action_server.py:46-48 waits for all first)
+            pending = list(range(n_worker))
+            while pending:
+                progressed = False
+                for w in list(pending):
+                    if obs_ready[w].acquire(block=False):
+                        ro.upload_worker_rows(t, w)
+                        pending.remove(w)
+                        progressed = True
+                if pending and not progressed:
+                    w = pending.pop(0)
+                    obs_ready[w].acquire()
+                    ro.upload_worker_rows(t, w)
             t1 = clock() if prof is not None else 0.0
             done_now = step_np.done
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=b)
-            ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset)
+            ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset, obs_done=True)
             t2 = clock() if prof is not None else 0.0
             for s in act_ready:
                 s.release()

@@ -108,8 +108,8 @@ class DeviceRollout:
             torch.cuda.current_stream(self.device).synchronize()                  # actions are on the host
 
     # ---- one env step = upload + agent.step + record (+ D2H), optionally replayed as a CUDA graph ----
-    def _step_body(self, k, zero_inputs_on_done, blank_done_rows):
-        obs_dev = self.upload(k, zero_inputs_on_done)
+    def _step_body(self, k, zero_inputs_on_done, blank_done_rows, obs_done=False):
+        obs_dev = self.upload(k, zero_inputs_on_done, obs_done=obs_done)
         if k == 0:
             self.begin_batch()
         self.act(k, obs_dev, blank_done_rows=blank_done_rows, sync=False)
@@ -174,10 +174,11 @@ class DeviceRollout:
     def wait(self):
         (self.side_stream or torch.cuda.current_stream(self.device)).synchronize()
 
-    def step(self, k, zero_inputs_on_done, blank_done_rows=False):
-        """Event k in [0,T): observation(k) is in the step buffer -> actions are on the host on return."""
-        self._run((k, zero_inputs_on_done, blank_done_rows),
-                  lambda: self._step_body(k, zero_inputs_on_done, blank_done_rows))
+    def step(self, k, zero_inputs_on_done, blank_done_rows=False, obs_done=False):
+        """Event k in [0,T): observation(k) is in the step buffer (``obs_done``: already uploaded per worker by
+        ``upload_worker_rows``) -> actions are on the host on return."""
+        self._run((k, zero_inputs_on_done, blank_done_rows, obs_done),
+                  lambda: self._step_body(k, zero_inputs_on_done, blank_done_rows, obs_done))
         self.wait()
 
     def finish(self):
