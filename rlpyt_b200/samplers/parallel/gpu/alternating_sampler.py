@@ -91,6 +91,7 @@ class AlternatingSampler(GpuSampler):
         # of a half is done the rows of the others are already in HBM.  (Measured on the B200 host, profiles/
         # r02_sampler_halfstep.json: H2D of a half 100 us + agent.step 94 us were strictly serial per half, because the
         # other half's workers were never done yet when the master looked once right after launching agent.step.)
+        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "1") == "1"   # 0: one H2D per half once all its workers are done
         pending = [list(range(len(p))) for p in self.obs_ready_pair]   # workers whose obs_ready for the half's next event is still to be taken
         uploaded = [False, False]
         half_w = len(self.obs_ready_pair[0])
@@ -102,7 +103,8 @@ class AlternatingSampler(GpuSampler):
             while i < len(left):
                 w = left[i]
                 if sems[w].acquire(block=block):
-                    ro.upload_worker_rows(k, w)
+                    if chunked:
+                        ro.upload_worker_rows(k, w)
                     left.pop(i)
                 else:
                     i += 1
@@ -115,7 +117,7 @@ class AlternatingSampler(GpuSampler):
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=int(b) + sl.start)
-            ro.upload_async(k, zero_inputs_on_done=True, obs_done=True)     # reward / done / agent inputs
+            ro.upload_async(k, zero_inputs_on_done=True, obs_done=chunked)  # reward / done / agent inputs (+ observations if not chunked)
 
         for t in range(T):
             for alt in range(2):

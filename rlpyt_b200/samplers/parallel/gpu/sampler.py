@@ -231,6 +231,7 @@ class GpuSampler(BaseSampler):
         prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
         clock = time.perf_counter
         n_worker = len(obs_ready)
+        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "1") == "1"
         for t in range(T):
             t0 = clock() if prof is not None else 0.0
             # workers wrote obs(t), reward(t-1), done(t-1): each worker's rows go to HBM as soon as it has signalled,
@@ -240,19 +241,21 @@ class GpuSampler(BaseSampler):
                 progressed = False
                 for w in list(pending):
                     if obs_ready[w].acquire(block=False):
-                        ro.upload_worker_rows(t, w)
+                        if chunked:
+                            ro.upload_worker_rows(t, w)
                         pending.remove(w)
                         progressed = True
                 if pending and not progressed:
                     w = pending.pop(0)
                     obs_ready[w].acquire()
-                    ro.upload_worker_rows(t, w)
+                    if chunked:
+                        ro.upload_worker_rows(t, w)
             t1 = clock() if prof is not None else 0.0
             done_now = step_np.done
             if self.mid_batch_reset and np.any(done_now):
                 for b in np.where(done_now)[0]:
                     self.agent.reset_one(idx=b)
-            ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset, obs_done=True)
+            ro.step(t, zero_inputs_on_done=True, blank_done_rows=wait_reset, obs_done=chunked)
             t2 = clock() if prof is not None else 0.0
             for s in act_ready:
                 s.release()
