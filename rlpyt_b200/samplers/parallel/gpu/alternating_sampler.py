@@ -92,6 +92,7 @@ class AlternatingSampler(GpuSampler):
         # r02_sampler_halfstep.json: H2D of a half 100 us + agent.step 94 us were strictly serial per half, because the
         # other half's workers were never done yet when the master looked once right after launching agent.step.)
         chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "1") == "1"   # 0: one H2D per half once all its workers are done
+        poll_mode = os.environ.get("RLPYT_B200_SAMPLER_POLL", "spin")        # spin | once | yield: how the master looks at the stepping half while agent.step runs
         pending = [list(range(len(p))) for p in self.obs_ready_pair]   # workers whose obs_ready for the half's next event is still to be taken
         uploaded = [False, False]
         half_w = len(self.obs_ready_pair[0])
@@ -136,8 +137,10 @@ class AlternatingSampler(GpuSampler):
                         if poll(other, t_other, False):
                             finish_upload(other, t_other)
                             uploaded[other] = True
-                        elif ro.act_done():
+                        elif poll_mode == "once" or ro.act_done():
                             break
+                        elif poll_mode == "yield":
+                            os.sched_yield()
                 tb = clock() if prof is not None else 0.0
                 ro.wait()                                    # actions of this half are in the step buffer
                 t2 = clock() if prof is not None else 0.0
