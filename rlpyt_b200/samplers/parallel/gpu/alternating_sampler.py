@@ -86,13 +86,17 @@ class AlternatingSampler(GpuSampler):
             current = torch.cuda.current_stream(self.device)
             for ro in self.rollouts:
                 ro.side_stream.wait_stream(current)          # the learner's last update is ordered before this batch
-        # Each half's observations are uploaded PER WORKER, as soon as that worker has signalled (rl_upload_async): the
-        # master polls the other half's workers while it waits for this half's agent.step, so by the time the last worker
-        # of a half is done the rows of the others are already in HBM.  (Measured on the B200 host, profiles/
-        # r02_sampler_halfstep.json: H2D of a half 100 us + agent.step 94 us were strictly serial per half, because the
-        # other half's workers were never done yet when the master looked once right after launching agent.step.)
-        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "1") == "1"   # 0: one H2D per half once all its workers are done
-        poll_mode = os.environ.get("RLPYT_B200_SAMPLER_POLL", "spin")        # spin | once | yield: how the master looks at the stepping half while agent.step runs
+        # Optionally (RLPYT_B200_SAMPLER_CHUNKED=1, RLPYT_B200_SAMPLER_POLL=spin|yield) each half's observations are uploaded
+        # PER WORKER, as soon as that worker has signalled (rl_upload_async), with the master polling the other half's
+        # workers while it waits for this half's agent.step.  (profiles/r02_sampler_halfstep.json: H2D of a half 100 us +
+        # agent.step 94 us are otherwise serial per half - the other half's workers are never all done yet when the
+        # master looks once right after launching agent.step.)
+        # Measured on the B200 host (profiles/r02_sampler_poll_ab.txt): per-worker uploads + polling do take the H2D off the
+        # device critical path (device part of a step 333 -> 268 us) but the env workers lose the same time - the two groups
+        # sit on sibling hardware threads of the same 7 cores and now overlap more - so the defaults stay "one upload per
+        # half, look once"; the switches remain for hosts with more cores per GPU.
+        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "0") == "1"   # 1: each worker's rows are uploaded as it signals
+        poll_mode = os.environ.get("RLPYT_B200_SAMPLER_POLL", "once")        # once | spin | yield: how the master looks at the stepping half while agent.step runs
         pending = [list(range(len(p))) for p in self.obs_ready_pair]   # workers whose obs_ready for the half's next event is still to be taken
         uploaded = [False, False]
         half_w = len(self.obs_ready_pair[0])

@@ -231,7 +231,7 @@ class GpuSampler(BaseSampler):
         prof = self.profile if os.environ.get("RLPYT_B200_SAMPLER_PROFILE") == "1" else None
         clock = time.perf_counter
         n_worker = len(obs_ready)
-        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "1") == "1"
+        chunked = os.environ.get("RLPYT_B200_SAMPLER_CHUNKED", "0") == "1"   # 1: upload each worker's rows as it signals (see AlternatingSampler)
         for t in range(T):
             t0 = clock() if prof is not None else 0.0
             # workers wrote obs(t), reward(t-1), done(t-1): each worker's rows go to HBM as soon as it has signalled,

@@ -176,8 +176,8 @@ def test_config1_serial_a2c_cartpole():
     assert algo.update_counter == 20
 
 
-@pytest.mark.parametrize("kind", ["gpu", "alternating", "gpu_wait_reset", "serial"])
-def test_samplers_match_reference_sampler_golden(kind, golden):
+@pytest.mark.parametrize("kind", ["gpu", "alternating", "gpu_wait_reset", "serial", "gpu+chunked", "alternating+chunked"])
+def test_samplers_match_reference_sampler_golden(kind, golden, monkeypatch):
     """Field-by-field parity with the REFERENCE's samplers (tests/golden/collector.npz: rlpyt's GpuSampler,
     GpuSampler + GpuWaitResetCollector and SerialSampler stepping the same seeded synthetic envs under the
     deterministic policy of tests/deterministic_agent.py, three consecutive batches): observations, actions, rewards,
@@ -187,6 +187,10 @@ def test_samplers_match_reference_sampler_golden(kind, golden):
     standard GPU sampler's batch."""
     import os
     import sys
+    if kind.endswith("+chunked"):        # per-worker observation uploads (rl_upload_async) + polling master
+        kind = kind[:-len("+chunked")]
+        monkeypatch.setenv("RLPYT_B200_SAMPLER_CHUNKED", "1")
+        monkeypatch.setenv("RLPYT_B200_SAMPLER_POLL", "spin")
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from deterministic_agent import make_agent_class
     from rlpyt_b200.agents.base import AgentStep

@@ -133,9 +133,12 @@ class _FakeRollout:
         self.log.append((self.tag, "rows", k, i))
 
     def upload_async(self, t, zero_inputs_on_done, obs_done=False):
-        assert obs_done, "the alternating master uploads observations per worker"
-        assert sorted(e[3] for e in self.log if e[:3] == (self.tag, "rows", t)) == list(range(len(self.chunks)))
-        self.obs_seen.append(self._cur.pop(t))
+        if obs_done:                                      # RLPYT_B200_SAMPLER_CHUNKED=1: every worker's rows were uploaded one by one
+            assert sorted(e[3] for e in self.log if e[:3] == (self.tag, "rows", t)) == list(range(len(self.chunks)))
+            self.obs_seen.append(self._cur.pop(t))
+        else:                                             # one DMA of the half's whole step buffer, now
+            assert not any(e[:3] == (self.tag, "rows", t) for e in self.log)
+            self.obs_seen.append(self.step_np.observation.copy())
         self.log.append((self.tag, "up", t))
 
     def act_async(self, t, blank_done_rows=False):
@@ -161,14 +164,17 @@ class _FakeRollout:
         pass
 
 
-@pytest.mark.parametrize("kind", ["futex", "hybrid"])
-def test_alternating_master_loop_against_real_workers(kind):
+@pytest.mark.parametrize("kind,chunked,poll", [("futex", "0", "once"), ("hybrid", "0", "once"), ("futex", "1", "spin"),
+                                               ("hybrid", "1", "yield"), ("futex", "1", "once")])
+def test_alternating_master_loop_against_real_workers(kind, chunked, poll, monkeypatch):
     """``AlternatingSampler.serve_actions`` (the only new logic of that class) with the real forked worker loop:
     strict (half 0, half 1) alternation per step, no deadlock, all handshakes drained, and each half's
     observations equal a host replay of its envs under the actions the master chose."""
     import torch
     from rlpyt_b200.samplers.collections import BatchSpec
     from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler
+    monkeypatch.setenv("RLPYT_B200_SAMPLER_CHUNKED", chunked)     # per-worker uploads or one upload per half
+    monkeypatch.setenv("RLPYT_B200_SAMPLER_POLL", poll)           # how the master looks at the stepping half
     n_worker, n_envs, T, seed = 4, 2, 10, 11
     B = n_worker * n_envs
     step = StepBuffer(observation=_shared((B,) + IMG, np.uint8), action=_shared((B,), np.int64),
