@@ -301,6 +301,13 @@ int rl_conv2_wgrad_tc(const float* x, const float* out, const float* grad_out, f
 int rl_conv1_u8_i8_supported(int C, int H, int W);
 int rl_conv1_u8_forward_i8(const uint8_t* obs, const int64_t* rows, const float* weight, const float* bias,
                            float* out, int64_t N, int C, int H, int W, int relu, void* stream);
+/* The sampler's variant of the forward: the frames are read straight out of PAGE-LOCKED, device-mapped HOST memory
+ * (the step buffer the env workers write, rlpyt/samplers/parallel/gpu/collectors.py:38) by the kernel's bulk copies and
+ * are ALSO written to obs_copy ([N,C,H,W] u8 in HBM = observation[t] of the [T,B] batch) by one bulk store per frame, so
+ * the observations cross PCIe once and no host->device copy stands in front of agent.step
+ * (rlpyt/samplers/parallel/gpu/action_server.py:46-55 copies, then steps). */
+int rl_conv1_u8_forward_i8_stream(const uint8_t* obs_host_mapped, const float* weight, const float* bias, float* out,
+                                  uint8_t* obs_copy, int64_t N, int C, int H, int W, int relu, void* stream);
 int64_t rl_conv1_u8_wgrad_i8_scratch_bytes(void);
 int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
                          float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,

@@ -69,6 +69,7 @@ SIGNATURES = {
     "rl_conv2_wgrad_tc": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
     "rl_conv1_u8_i8_supported": (c_int, [c_int, c_int, c_int]),
     "rl_conv1_u8_forward_i8": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "rl_conv1_u8_forward_i8_stream": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "rl_conv1_u8_wgrad_i8_scratch_bytes": (c_int64, []),
     "rl_conv1_u8_wgrad_i8": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
     "rl_conv2_s2d_supported": (c_int, [c_int, c_int, c_int]),

@@ -6,7 +6,7 @@ from rlpyt_b200.agents.base import AgentStep, AlternatingRecurrentAgentMixin, Ba
 from rlpyt_b200.agents.pg.base import AgentInfo, AgentInfoRnn
 from rlpyt_b200.distributions.categorical import Categorical, DistInfo
 from rlpyt_b200.utils.buffer import buffer_func, buffer_method, buffer_to
-from rlpyt_b200.utils.gather import LazyRows
+from rlpyt_b200.utils.gather import HostMappedFrames, LazyRows
 
 
 class CategoricalPgAgent(BaseAgent):
@@ -18,7 +18,7 @@ class CategoricalPgAgent(BaseAgent):
 
     def _model_inputs(self, observation, prev_action, prev_reward):
         prev_action = self.distribution.to_onehot(prev_action)  # categorical.py:21,35
-        if isinstance(observation, LazyRows):  # un-gathered minibatch rows, already on the device
+        if isinstance(observation, (LazyRows, HostMappedFrames)):  # un-gathered minibatch rows / frames the first layer streams in itself
             return (observation,) + buffer_to((prev_action, prev_reward), device=self.device)
         return buffer_to((observation, prev_action, prev_reward), device=self.device)
 

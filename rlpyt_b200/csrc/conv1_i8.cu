@@ -33,6 +33,26 @@ int rl_conv1_u8_forward_i8(const uint8_t* obs, const int64_t* rows, const float*
     return RL_OK;
 }
 
+int rl_conv1_u8_forward_i8_stream(const uint8_t* obs_host_mapped, const float* weight, const float* bias, float* out,
+                                  uint8_t* obs_copy, int64_t N, int C, int H, int W, int relu, void* stream) {
+    RL_REQUIRE(obs_host_mapped && weight && bias && out && obs_copy, RL_EINVAL, "rl_conv1_u8_forward_i8_stream: null pointer");
+    RL_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && geom_ok(C, H, W), RL_EINVAL,
+               "rl_conv1_u8_forward_i8_stream: needs C=4, H %% 4 == 0, W %% 4 == 0, W <= 128 (got C=%d H=%d W=%d)", C, H, W);
+    RL_REQUIRE(rl::aligned(obs_host_mapped, 16) && rl::aligned(obs_copy, 16), RL_EALIGN,
+               "rl_conv1_u8_forward_i8_stream: frames must be 16-byte aligned (bulk copies)");
+    if (N == 0) return RL_OK;
+    const Geom g = make_geom(N, H, W);
+    RL_REQUIRE(smem_ok(g), RL_EINVAL, "rl_conv1_u8_forward_i8_stream: frame too large for the shared-memory ring (%dx%d)", H, W);
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    const cudaError_t e = launch_fwd(obs_host_mapped, nullptr, weight, bias, out, g, relu, sms, rl::as_stream(stream), obs_copy);
+    if (e != cudaSuccess) {
+        rl::set_error("rl_conv1_u8_forward_i8_stream: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    return RL_OK;
+}
+
 int64_t rl_conv1_u8_wgrad_i8_scratch_bytes(void) {
     int sms = rl::sm_count();
     if (sms <= 0) sms = 148;

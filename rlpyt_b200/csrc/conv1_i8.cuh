@@ -158,7 +158,7 @@ __device__ __forceinline__ void stage_tile(const Geom& g, uint32_t raw_base, uin
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv1_i8_fwd_kernel(const uint8_t* __restrict__ X, const int64_t* __restrict__ rows, const float* __restrict__ Wg,
-                    const float* __restrict__ bias, float* __restrict__ Y, Geom g, int relu) {
+                    const float* __restrict__ bias, float* __restrict__ Y, Geom g, int relu, uint8_t* __restrict__ copy_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const SmemLayout L(g.raw_stage_bytes);
@@ -220,6 +220,17 @@ conv1_i8_fwd_kernel(const uint8_t* __restrict__ X, const int64_t* __restrict__ r
             const int rs = i % kRaw;
             mbar_wait(&raw_full[rs], (i / kRaw) & 1);
             const uint32_t raw_base = raw_u32 + static_cast<uint32_t>(rs) * g.raw_stage_bytes + src_ch;
+            // copy_out: the frame that just landed in shared memory also goes to HBM (frame n of copy_out) by one bulk
+            // store - the sampler's step: frames stream in from the page-locked step buffer over PCIe ONCE, feeding
+            // both agent.step's first layer and observation[t] of the resident [T,B] batch (no separate H2D in front
+            // of the network).
+            const bool storer = copy_out != nullptr && warp == 0 && lane == 0;
+            if (storer) {
+                const int64_t n = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(copy_out + n * g.img_bytes)),
+                             "r"(raw_u32 + static_cast<uint32_t>(rs) * g.raw_stage_bytes), "r"(g.img_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             for (int t = 0; t < g.n_tiles; ++t, ++it) {
                 const int slot = it % kASlots;
                 stage_tile<3>(g, raw_base, a_u32 + static_cast<uint32_t>(slot * kSlotBytes), t, c, gpar, 2, lane,
@@ -228,6 +239,7 @@ conv1_i8_fwd_kernel(const uint8_t* __restrict__ X, const int64_t* __restrict__ r
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[slot]);
             }
+            if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage may be refilled once the store has read it
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);
         }
@@ -334,7 +346,7 @@ inline Geom make_geom(int64_t N, int H, int W) {
 inline bool smem_ok(const Geom& g) { return SmemLayout(g.raw_stage_bytes).total <= 232448u; }
 
 inline cudaError_t launch_fwd(const uint8_t* X, const int64_t* rows, const float* W, const float* bias, float* Y,
-                              const Geom& g, int relu, int sms, cudaStream_t st) {
+                              const Geom& g, int relu, int sms, cudaStream_t st, uint8_t* copy_out = nullptr) {
     const SmemLayout L(g.raw_stage_bytes);
     static uint32_t attr_bytes = 0;
     if (L.total > attr_bytes) {
@@ -343,7 +355,7 @@ inline cudaError_t launch_fwd(const uint8_t* X, const int64_t* rows, const float
         attr_bytes = L.total;
     }
     const int grid = g.n_img < sms ? g.n_img : sms;
-    conv1_i8_fwd_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(X, rows, W, bias, Y, g, relu);
+    conv1_i8_fwd_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(X, rows, W, bias, Y, g, relu, copy_out);
     return cudaGetLastError();
 }
 

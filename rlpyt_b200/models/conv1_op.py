@@ -6,6 +6,7 @@ Default implementation "i8": the integer tensor-core kernels of csrc/conv1_i8.cu
 the geometry fits (H, W multiples of 4, W <= 128); otherwise "tc", the TF32 implicit-GEMM kernels of
 csrc/conv_tc.cu.  ``RLPYT_B200_CONV1_FWD`` / ``RLPYT_B200_CONV_WGRAD`` = i8 | tc | simt select one explicitly
 (simt = the fp32 kernels of csrc/conv1.cu, kept for cross-checks)."""
+import ctypes
 import os
 
 import torch
@@ -113,3 +114,23 @@ class Conv1U8Relu(torch.autograd.Function):
 
 def conv1_u8_relu(weight, bias, obs, rows=None):
     return Conv1U8Relu.apply(weight, bias, obs, rows)
+
+
+def stream_supported(C, H, W):
+    """Can ``conv1_u8_relu_stream`` take this geometry (the kind::i8 kernel must be the dispatched forward)?"""
+    return _impl(FORWARD_IMPL, C, H, W) == "i8"
+
+
+@torch.no_grad()
+def conv1_u8_relu_stream(weight, bias, frames):
+    """Forward only (``agent.step``): ``frames`` = ``HostMappedFrames``; the kernel reads them from page-locked host memory
+    and records them in ``frames.copy_to`` while computing the layer."""
+    N, C, H, W = frames.shape
+    OH, OW = (H - 8) // 4 + 1, (W - 8) // 4 + 1
+    dev = frames.copy_to.device
+    w, b = weight.detach().contiguous(), bias.detach().contiguous()
+    out = torch.empty((N, 16, OH, OW), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("rl_conv1_u8_forward_i8_stream", ctypes.c_void_p(frames.host_ptr), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
+                  _lib.ptr(frames.copy_to), N, C, H, W, 1, _lib.stream())
+    return out

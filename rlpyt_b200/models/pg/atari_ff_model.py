@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from rlpyt_b200.models import conv1_op, conv2_op, gemm_op
 from rlpyt_b200.models.conv2d import Conv2dHeadModel
-from rlpyt_b200.utils.gather import LazyRows
+from rlpyt_b200.utils.gather import HostMappedFrames, LazyRows
 from rlpyt_b200.utils.tensor import infer_leading_dims, restore_leading_dims
 
 
@@ -37,6 +37,10 @@ class AtariFfModel(torch.nn.Module):
         self.fused_first_layer = conv1_op.supported(self.image_shape, layers)
         self.tc_second_layer = len(layers) == 4 and conv2_op.supported(layers[2], layers[3])
         self.accepts_lazy_rows = True
+        # agent.step may be handed frames that still lie in the page-locked step buffer (HostMappedFrames): the first
+        # layer streams them over PCIe itself and records them in HBM on the way (conv1_op.conv1_u8_relu_stream)
+        self.accepts_host_mapped_frames = bool(self.fused_first_layer and len(self.image_shape) == 3
+                                               and conv1_op.stream_supported(*self.image_shape))
 
     def _fused_forward(self, obs, rows, lead_shape):
         layers = self.conv.conv.conv
@@ -72,10 +76,16 @@ class AtariFfModel(torch.nn.Module):
         from rlpyt_b200 import _lib
         from rlpyt_b200.distributions.categorical import DistInfo
         A = self.pi.out_features
-        if (self.fused_first_layer and isinstance(image, torch.Tensor) and image.dtype == torch.uint8 and image.is_cuda
-                and image.is_contiguous() and image.dim() == 4 and A <= 32 and hasattr(distribution, "_rng_state")):
+        mapped = isinstance(image, HostMappedFrames)
+        if mapped and not (self.accepts_host_mapped_frames and A <= 32 and hasattr(distribution, "_rng_state")):
+            raise ValueError("HostMappedFrames need the fused kind::i8 first layer and the fused policy head")
+        if mapped or (self.fused_first_layer and isinstance(image, torch.Tensor) and image.dtype == torch.uint8 and image.is_cuda
+                      and image.is_contiguous() and image.dim() == 4 and A <= 32 and hasattr(distribution, "_rng_state")):
             layers = self.conv.conv.conv
-            x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, image, None)
+            if mapped:
+                x = conv1_op.conv1_u8_relu_stream(layers[0].weight, layers[0].bias, image)
+            else:
+                x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, image, None)
             x = conv2_op.conv2_relu(x, layers[2].weight, layers[2].bias) if self.tc_second_layer else layers[2:](x)
             h = self._head(x.view(x.shape[0], -1)).contiguous()
             Bn, F_ = h.shape

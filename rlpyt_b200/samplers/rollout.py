@@ -35,6 +35,14 @@ class DeviceRollout:
         self.use_graphs = os.environ.get("RLPYT_B200_SAMPLER_GRAPHS", "1") == "1"
         self._warned_unpinned = False
         self.capture_error_mode = "global"
+        # RLPYT_B200_SAMPLER_ZEROCOPY=1: no H2D of the observations in front of agent.step - the first layer reads the
+        # frames out of the page-locked step buffer itself and records them in observation[t] on the way (models that
+        # set ``accepts_host_mapped_frames``; feed-forward agents; the buffer must be page-locked)
+        self.zero_copy = (os.environ.get("RLPYT_B200_SAMPLER_ZEROCOPY", "0") == "1" and bool(host.get("pinned", False))
+                          and bool(getattr(getattr(agent, "model", None), "accepts_host_mapped_frames", False))
+                          and not getattr(agent, "recurrent", False) and self.step_np.observation.dtype == np.uint8
+                          and self.step_np.observation.ndim == 4)
+        self._host_obs_ptr = int(self.step_np.observation.ctypes.data)
         self._act_event = None
         self._graphs = {}
         self._eager_batches = 0
@@ -74,7 +82,7 @@ class DeviceRollout:
         step buffer.  Record them at their [T,B] rows and stage the agent inputs."""
         s = self.samples
         obs_dst = self.obs_slot(k)
-        if not obs_done:
+        if not obs_done and not (self.zero_copy and k < self.T):   # zero-copy: agent.step's first layer brings the frames in
             obs_dst.copy_(self.step_pyt.observation, non_blocking=True)
         self.all_reward[k].copy_(self.step_pyt.reward, non_blocking=True)       # reward(k-1) = prev_reward(k)
         self.done_step.copy_(self.step_pyt.done, non_blocking=True)
@@ -94,6 +102,9 @@ class DeviceRollout:
     # ---- agent.step on resident data ---------------------------------------------------------------
     @torch.no_grad()
     def act(self, t, obs_dev, blank_done_rows=False, sync=True):
+        if self.zero_copy:
+            from rlpyt_b200.utils.gather import HostMappedFrames
+            obs_dev = HostMappedFrames(self._host_obs_ptr, self.obs_slot(t))
         step = self.agent.step(obs_dev, self.in_action, self.in_reward)
         action, agent_info = step.action, step.agent_info
         if blank_done_rows:  # wait-reset collectors record blanks for finished envs

@@ -69,3 +69,33 @@ class LazyRows:
 
     def materialize(self):
         return gather_rows(self.src, self.rows)
+
+
+class HostMappedFrames:
+    """uint8 frames ``[B,C,H,W]`` lying in PAGE-LOCKED host memory that the device can address (``cudaHostRegister`` /
+    pinned allocations under unified addressing: the host pointer is the device pointer), together with the HBM tensor
+    they are to be recorded in.  A first layer that streams its frames with bulk copies can read them from there and
+    write the HBM copy in the same pass (csrc/conv1_i8.cuh ``copy_out``): the sampler's per-step H2D disappears from in
+    front of ``agent.step``.  Quacks enough like a tensor for the agents' ``step`` plumbing."""
+
+    is_cuda = True
+
+    def __init__(self, host_ptr, copy_to):
+        _lib.require_cuda(copy_to)
+        assert copy_to.dtype == torch.uint8 and copy_to.is_contiguous() and copy_to.dim() == 4
+        self.host_ptr, self.copy_to = int(host_ptr), copy_to
+
+    @property
+    def shape(self):
+        return tuple(self.copy_to.shape)
+
+    @property
+    def dtype(self):
+        return torch.uint8
+
+    @property
+    def device(self):
+        return self.copy_to.device
+
+    def dim(self):
+        return 4

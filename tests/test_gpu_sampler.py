@@ -236,3 +236,65 @@ def test_samplers_match_reference_sampler_golden(kind, golden, monkeypatch):
                 assert sorted(int(t["Length"]) for t in traj_infos) == list(g[pre + "traj_lengths"])
     finally:
         sampler.shutdown()
+
+
+
+def test_first_layer_streams_frames_from_pinned_host_memory():
+    """csrc/conv1_i8.cuh ``copy_out`` (rl_conv1_u8_forward_i8_stream): frames read by the kernel's bulk copies straight
+    out of page-locked host memory give the same activations, bit for bit, as the same frames resident in HBM, and land
+    in the HBM copy unchanged."""
+    from rlpyt_b200.models import conv1_op
+    from rlpyt_b200.utils.gather import HostMappedFrames
+    g = torch.Generator().manual_seed(5)
+    for B in (1, 37, 128, 300):
+        host = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, generator=g).pin_memory()
+        w = (torch.randn(16, 4, 8, 8, generator=g) / 16).cuda()
+        b = torch.randn(16, generator=g).cuda()
+        copy = torch.zeros((B, 4, 84, 84), dtype=torch.uint8, device="cuda")
+        got = conv1_op.conv1_u8_relu_stream(w, b, HostMappedFrames(host.data_ptr(), copy))
+        want = conv1_op.conv1_u8_relu(w, b, host.cuda(), None)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), B
+        assert torch.equal(copy.cpu(), host), B
+
+
+@pytest.mark.parametrize("kind", ["gpu", "alternating", "serial"])
+def test_zero_copy_sampler_steps_match_the_uploading_sampler(kind, monkeypatch):
+    """RLPYT_B200_SAMPLER_ZEROCOPY=1 (agent.step's first layer reads the step buffer over PCIe and records
+    observation[t] itself, no H2D in front of it) leaves every field of three consecutive batches - the eager first
+    batch and the CUDA-graph replays - identical to the sampler that uploads first.  Same seeds, same Philox stream."""
+    from rlpyt_b200.agents.pg.atari import AtariFfAgent
+    from rlpyt_b200.envs.synthetic import SyntheticAtariEnv
+    from rlpyt_b200.samplers.parallel.gpu.alternating_sampler import AlternatingSampler
+    from rlpyt_b200.samplers.parallel.gpu.sampler import GpuSampler
+    from rlpyt_b200.samplers.serial.sampler import SerialSampler
+    cls = dict(gpu=GpuSampler, alternating=AlternatingSampler, serial=SerialSampler)[kind]
+    T, B = 6, 8
+
+    def run(zero_copy):
+        monkeypatch.setenv("RLPYT_B200_SAMPLER_ZEROCOPY", "1" if zero_copy else "0")
+        torch.manual_seed(0)
+        sampler = cls(EnvCls=SyntheticAtariEnv, env_kwargs=dict(image_shape=(4, 84, 84), n_actions=6, p_done=0.1, p_reward=0.3),
+                      batch_T=T, batch_B=B, max_decorrelation_steps=0)
+        agent = AtariFfAgent()
+        sampler.initialize(agent, affinity=dict(cuda_idx=0, workers_cpus=[None] * 4, set_affinity=False), seed=4, bootstrap_value=True)
+        agent.to_device(0)
+        ros = getattr(sampler, "rollouts", None) or [sampler.rollout]
+        assert all(ro.zero_copy == zero_copy for ro in ros)
+        out = []
+        try:
+            for itr in range(3):
+                samples, _ = sampler.obtain_samples(itr)
+                torch.cuda.synchronize()
+                out.append(dict(obs=samples.env.observation.cpu().clone(), action=samples.agent.action.cpu().clone(),
+                                prob=samples.agent.agent_info.dist_info.prob.cpu().clone(), value=samples.agent.agent_info.value.cpu().clone(),
+                                reward=samples.env.reward.cpu().clone(), done=samples.env.done.cpu().clone(),
+                                bv=samples.agent.bootstrap_value.cpu().clone()))
+        finally:
+            sampler.shutdown()
+        return out
+
+    a, b = run(False), run(True)
+    for itr, (x, y) in enumerate(zip(a, b)):
+        for k in x:
+            assert torch.equal(x[k], y[k]), (itr, k)
