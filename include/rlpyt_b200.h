@@ -253,6 +253,11 @@ int rl_gemm_tf32x3_f32(const float* A, const float* B, const float* bias, float*
 int64_t rl_gemm_ts_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int rl_gemm_ts_f32(const float* A, int a_mmajor, const float* B, const float* B_lo, const float* bias, float* C,
                    int c_trans, int64_t M, int64_t N, int64_t K, int relu, void* workspace, void* stream);
+/* The input gradient of a Linear layer whose INPUT is the output of a ReLU (rlpyt/models/conv2d.py:41 feeding
+ * rlpyt/models/mlp.py:30-36): C[M,N] = (A[M,K] @ B[N,K]^T) where out_mask[M,N] > 0, else 0 - the ReLU backward of the
+ * preceding layer folded into the GEMM's epilogue (out_mask = that layer's output, same layout as C). */
+int rl_gemm_ts_masked_f32(const float* A, const float* B, const float* B_lo, const float* out_mask, float* C, int64_t M,
+                          int64_t N, int64_t K, void* workspace, void* stream);
 /* lo[i] = src[i] - trunc_tf32(src[i]);  dst = src^T ([cols,rows]) and dst_lo = dst - trunc_tf32(dst) */
 int rl_split_lo_f32(const float* src, float* lo, int64_t n, void* stream);
 int rl_transpose_split_f32(const float* src, float* dst, float* dst_lo, int64_t rows, int64_t cols, void* stream);

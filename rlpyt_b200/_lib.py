@@ -54,6 +54,7 @@ SIGNATURES = {
     "rl_gemm_tf32x3_f32": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int, P, P]),
     "rl_gemm_ts_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "rl_gemm_ts_f32": (c_int, [P, c_int, P, P, P, P, c_int, c_int64, c_int64, c_int64, c_int, P, P]),
+    "rl_gemm_ts_masked_f32": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, P, P]),
     "rl_split_lo_f32": (c_int, [P, P, c_int64, P]),
     "rl_transpose_split_f32": (c_int, [P, P, P, c_int64, c_int64, P]),
     "rl_conv1_u8_forward_tc": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),

@@ -28,6 +28,23 @@ int rl_gemm_ts_f32(const float* A, int a_mmajor, const float* B, const float* B_
     return rl::check_launch("gemm_ts_kernel");
 }
 
+int rl_gemm_ts_masked_f32(const float* A, const float* B, const float* B_lo, const float* out_mask, float* C, int64_t M,
+                          int64_t N, int64_t K, void* workspace, void* stream) {
+    RL_REQUIRE(A && B && B_lo && C && out_mask, RL_EINVAL, "rl_gemm_ts_masked_f32: null pointer");
+    RL_REQUIRE(M >= 1 && N >= 1 && K >= 1 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), RL_EINVAL,
+               "rl_gemm_ts_masked_f32: M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    RL_REQUIRE(K % 4 == 0, RL_EALIGN, "rl_gemm_ts_masked_f32: row pitches must be multiples of 16 bytes (K %% 4 == 0)");
+    RL_REQUIRE(rl::aligned(A, 16) && rl::aligned(B, 16) && rl::aligned(B_lo, 16) && rl::aligned(C, 16) && rl::aligned(out_mask, 16) &&
+                   (workspace == nullptr || rl::aligned(workspace, 16)),
+               RL_EALIGN, "rl_gemm_ts_masked_f32: 16-byte aligned A, B, B_lo, C, out_mask, workspace required");
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    const cudaError_t e = rl::gts::launch(A, 0, B, B_lo, nullptr, C, 0, M, N, K, 0, static_cast<float*>(workspace), sms,
+                                          rl::as_stream(stream), out_mask);
+    RL_REQUIRE(e != cudaErrorInvalidValue, RL_EINVAL, "rl_gemm_ts_masked_f32: cuTensorMapEncodeTiled unavailable or failed");
+    return rl::check_launch("gemm_ts_kernel");
+}
+
 int rl_split_lo_f32(const float* src, float* lo, int64_t n, void* stream) {
     if (n == 0) return RL_OK;
     RL_REQUIRE(src && lo && n > 0, RL_EINVAL, "rl_split_lo_f32: null pointer or negative n");

@@ -55,6 +55,8 @@ constexpr uint32_t kIdesc = tc::make_idesc_tf32(BM, BN);
 struct Params {
     float* C;              // [M,N] (or [N,M] when c_trans); with splits > 1: workspace [splits][...] in the same layout
     const float* bias;     // [N] or nullptr (applied here only when splits == 1)
+    const float* mask;     // [M,N] or nullptr: result element kept where mask > 0, else 0 (the ReLU backward of the layer
+                           // that produced this GEMM's gradient input, fused into the epilogue; not with c_trans)
     int M, N, K;
     int relu;
     int c_trans;
@@ -260,6 +262,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* dst = p.C + (p.splits > 1 ? static_cast<int64_t>(z) * MN : 0);
             const float* bias = p.splits > 1 ? nullptr : p.bias;
             const bool relu = p.splits == 1 && p.relu;
+            const float* mask = p.splits > 1 ? nullptr : p.mask;
             if (p.c_trans) {
 #pragma unroll
                 for (int j = 0; j < BN; ++j) {
@@ -272,16 +275,29 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             } else if (row < p.M) {
                 float* out = dst + static_cast<int64_t>(row) * p.N + n0;
+                const float* mrow = mask != nullptr ? mask + static_cast<int64_t>(row) * p.N + n0 : nullptr;
                 const bool vec_ok = (p.N % 4 == 0);
 #pragma unroll
                 for (int j = 0; j < BN; j += 4) {
                     const int n = n0 + j;
                     float o[4];
+                    float mk[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+                    if (mrow != nullptr) {
+                        if (vec_ok && n + 3 < p.N) {
+                            const float4 m4 = *reinterpret_cast<const float4*>(mrow + j);
+                            mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < p.N) mk[e] = mrow[j + e];
+                        }
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float x = acc[j + e];
                         if (bias != nullptr && n + e < p.N) x += bias[n + e];
-                        o[e] = relu ? fmaxf(x, 0.0f) : x;
+                        x = relu ? fmaxf(x, 0.0f) : x;
+                        o[e] = mk[e] > 0.0f ? x : 0.0f;
                     }
                     if (vec_ok && n + 3 < p.N) {
                         *reinterpret_cast<float4*>(out + j) = make_float4(o[0], o[1], o[2], o[3]);
@@ -307,13 +323,14 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // [M,N] (bias index i % N) or, c_trans, [N,M] (bias index i / M).
 __global__ void __launch_bounds__(256)
 ts_splitk_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ bias, float* __restrict__ out,
-                        int64_t MN, int M, int N, int relu, int c_trans) {
+                        int64_t MN, int M, int N, int relu, int c_trans, const float* __restrict__ mask) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= MN) return;
     float s = 0.0f;
     for (int z = 0; z < splits; ++z) s += ws[static_cast<int64_t>(z) * MN + i];
     if (bias != nullptr) s += bias[c_trans ? i / M : i % N];
-    out[i] = relu ? fmaxf(s, 0.0f) : s;
+    s = relu ? fmaxf(s, 0.0f) : s;
+    out[i] = (mask == nullptr || mask[i] > 0.0f) ? s : 0.0f;
 }
 
 // lo = x - trunc_tf32(x), elementwise (the B operand's second term)
@@ -417,7 +434,7 @@ static inline int64_t workspace_bytes(int64_t M, int64_t N, int64_t K, int sms) 
 // Returns cudaSuccess / the launch error; cudaErrorInvalidValue when the tensor maps cannot be built.
 static inline cudaError_t launch(const float* A, int a_mmajor, const float* B, const float* B_lo, const float* bias, float* C,
                                  int c_trans, int64_t M, int64_t N, int64_t K, int relu, float* workspace, int sms,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const float* mask = nullptr) {
     CUtensorMap ma, mb, mlo;
     const bool ok_a = a_mmajor ? make_map(&ma, A, K, M, BK, BM) : make_map(&ma, A, M, K, BM, BK);
     if (!ok_a || !make_map(&mb, B, N, K, BN, BK) || !make_map(&mlo, B_lo, N, K, BN, BK)) return cudaErrorInvalidValue;
@@ -430,6 +447,7 @@ static inline cudaError_t launch(const float* A, int a_mmajor, const float* B, c
     const Plan pl = make_plan(M, N, K, sms, workspace != nullptr);
     Params p;
     p.C = pl.splits > 1 ? workspace : C;
+    p.mask = mask;
     p.bias = bias; p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
     p.relu = relu; p.c_trans = c_trans; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
     p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n;
@@ -439,7 +457,7 @@ static inline cudaError_t launch(const float* A, int a_mmajor, const float* B, c
     if (e != cudaSuccess || pl.splits == 1) return e;
     const int64_t MN = M * N;
     ts_splitk_reduce_kernel<<<static_cast<unsigned>((MN + 255) / 256), 256, 0, st>>>(
-        workspace, pl.splits, bias, C, MN, static_cast<int>(M), static_cast<int>(N), relu, c_trans);
+        workspace, pl.splits, bias, C, MN, static_cast<int>(M), static_cast<int>(N), relu, c_trans, mask);
     return cudaGetLastError();
 }
 

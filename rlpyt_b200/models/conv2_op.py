@@ -41,8 +41,11 @@ def supported(layer, act):
 class Conv2ReluTC(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, grad_is_masked=False):
+        """``grad_is_masked``: the consumer of the output applies this layer's ReLU backward itself (the fc layer's
+        input-gradient GEMM zeroes its result where this output is <= 0): ``backward`` must not do it a second time."""
         _lib.require_cuda(x, weight, bias)
+        ctx.grad_is_masked = bool(grad_is_masked)
         x = x.contiguous()
         N, C, IH, IW = x.shape
         OH, OW = (IH - 2) // 2 + 1, (IW - 2) // 2 + 1
@@ -57,7 +60,7 @@ class Conv2ReluTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight, out = ctx.saved_tensors
-        g = relu_backward(grad_out, out)
+        g = grad_out.contiguous() if ctx.grad_is_masked else relu_backward(grad_out, out)
         gx = gw = gb = None
         N, C, IH, IW = x.shape
         if ctx.needs_input_grad[0] and s2d_supported(C, IH, IW):
@@ -98,8 +101,8 @@ class Conv2ReluTC(torch.autograd.Function):
             _gx, gw, gb = torch.ops.aten.convolution_backward(
                 g, x, weight, [32], [2, 2], [1, 1], [1, 1], False, [0, 0], 1,
                 [False, ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
-def conv2_relu(x, weight, bias):
-    return Conv2ReluTC.apply(x, weight, bias)
+def conv2_relu(x, weight, bias, grad_is_masked=False):
+    return Conv2ReluTC.apply(x, weight, bias, grad_is_masked)

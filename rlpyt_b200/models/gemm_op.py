@@ -50,16 +50,23 @@ def transpose_split(x):
     return dst, lo
 
 
-def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False):
+def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False, out_mask=None):
     """a @ b^T (+bias) (+relu).  a: [M,K], or with ``a_mmajor`` the [K,M] matrix a^T; b, b_lo: [N,K];
-    result [M,N], or with ``c_trans`` its transpose [N,M]."""
-    _lib.require_cuda(a, b, b_lo, bias)
+    result [M,N], or with ``c_trans`` its transpose [N,M].  ``out_mask`` [M,N]: result kept where ``out_mask > 0``, zero
+    elsewhere (a preceding ReLU's backward folded into the epilogue; plain form only)."""
+    _lib.require_cuda(a, b, b_lo, bias, out_mask)
     a, b, b_lo = a.contiguous(), b.contiguous(), b_lo.contiguous()
     (K, M) = a.shape if a_mmajor else a.shape[::-1]
     N = b.shape[0]
     assert b.shape == (N, K) and b_lo.shape == (N, K) and a.dtype == b.dtype == b_lo.dtype == torch.float32
     out = torch.empty((N, M) if c_trans else (M, N), dtype=torch.float32, device=a.device)
     ws = _workspace(a.device, int(_lib.load().rl_gemm_ts_workspace_bytes(M, N, K)))
+    if out_mask is not None:
+        assert not (a_mmajor or c_trans or relu) and bias is None and tuple(out_mask.shape) == (M, N) and out_mask.is_contiguous()
+        with torch.cuda.device(a.device):
+            _lib.call("rl_gemm_ts_masked_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(b_lo), _lib.ptr(out_mask), _lib.ptr(out), M, N, K,
+                      _lib.ptr(ws), _lib.stream(), n_launch=2 if ws is not None else 1)
+        return out
     with torch.cuda.device(a.device):
         _lib.call("rl_gemm_ts_f32", _lib.ptr(a), int(bool(a_mmajor)), _lib.ptr(b), _lib.ptr(b_lo), _lib.ptr(bias), _lib.ptr(out),
                   int(bool(c_trans)), M, N, K, int(bool(relu)), _lib.ptr(ws), _lib.stream(), n_launch=2 if ws is not None else 1)
@@ -113,8 +120,13 @@ def _use_ts(m):
 class LinearTf32x3(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
+    def forward(ctx, x, weight, bias, relu, input_is_relu_output=False):
+        """``input_is_relu_output``: ``x`` is the output of a ReLU and the caller wants that ReLU's backward applied HERE
+        (grad_x zeroed where x <= 0, in the input-gradient GEMM's epilogue) - the producer of ``x`` must then not apply
+        it again.  Only honoured on the ``gemm_ts`` path (``fuses_input_relu``)."""
         b = None if bias is None else bias.detach().contiguous()
+        ctx.input_relu = bool(input_is_relu_output)
+        assert not ctx.input_relu or _use_ts(x.shape[0]), "input ReLU fusion needs the gemm_ts path"
         if _use_ts(x.shape[0]):
             w = weight.detach()
             y = gemm_ts(x.detach(), w, split_lo(w), b, relu)
@@ -136,7 +148,8 @@ class LinearTf32x3(torch.autograd.Function):
         ts = _use_ts(M)
         if ctx.needs_input_grad[0]:
             if ts:
-                gx = gemm_ts(gy, *transpose_split(weight.detach()))       # [M,N] x [K,N]^T
+                gx = gemm_ts(gy, *transpose_split(weight.detach()),       # [M,N] x [K,N]^T
+                             out_mask=x.detach() if ctx.input_relu else None)
             else:
                 gx = gemm_tn(gy, transpose2d(weight.detach()))
         if ctx.needs_input_grad[1]:
@@ -150,8 +163,13 @@ class LinearTf32x3(torch.autograd.Function):
                 gw = gemm_tn(transpose2d(gy), transpose2d(x.detach()))   # [N,M] x [K,M]^T
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear_tf32x3(x, weight, bias=None, relu=False):
-    return LinearTf32x3.apply(x, weight, bias, relu)
+def fuses_input_relu(m):
+    """Will ``linear_tf32x3(x[m, :], ..., input_is_relu_output=True)`` apply the input's ReLU backward itself?"""
+    return _use_ts(m)
+
+
+def linear_tf32x3(x, weight, bias=None, relu=False, input_is_relu_output=False):
+    return LinearTf32x3.apply(x, weight, bias, relu, input_is_relu_output)

@@ -5,6 +5,8 @@ Submodule names equal the reference's, so ``state_dict``s are interchangeable.  
 are converted with ``float(x) * (1/255)`` - one fp32 rounding, exactly the reference's
 ``img.type(float).mul_(1./255)`` (:50-51).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -45,11 +47,14 @@ class AtariFfModel(torch.nn.Module):
     def _fused_forward(self, obs, rows, lead_shape):
         layers = self.conv.conv.conv
         x = conv1_op.conv1_u8_relu(layers[0].weight, layers[0].bias, obs, rows)
+        # the ReLU backward of the second layer rides in the epilogue of the fc layer's input-gradient GEMM when both
+        # layers are on this package's kernels (one 315 MB elementwise pass less per update)
+        fuse = self.tc_second_layer and torch.is_grad_enabled() and self._head_fuses_input_relu(x.shape[0])
         if self.tc_second_layer:
-            x = conv2_op.conv2_relu(x, layers[2].weight, layers[2].bias)
+            x = conv2_op.conv2_relu(x, layers[2].weight, layers[2].bias, grad_is_masked=fuse)
         else:
             x = layers[2:](x)
-        fc_out = self._head(x.view(x.shape[0], -1))
+        fc_out = self._head(x.view(x.shape[0], -1), input_is_relu_output=fuse)
         pi = F.softmax(self.pi(fc_out), dim=-1)
         v = self.value(fc_out).squeeze(-1)
         return pi.view(lead_shape + pi.shape[1:]), v.view(lead_shape)
@@ -58,15 +63,26 @@ class AtariFfModel(torch.nn.Module):
     # is used - with split-K when the 128x128 tile grid cannot fill the 148 SMs (agent.step, M=256)
     TC_GEMM_MIN_ROWS = 64
 
-    def _head(self, flat):
-        """Linear(conv_out -> fc) + ReLU: the fp32-accurate tcgen05 GEMM for minibatch-sized inputs."""
+    def _head_mods(self):
         head = self.conv.head
         mods = list(head.model) if isinstance(head, torch.nn.Module) and hasattr(head, "model") else None
-        if (mods is not None and len(mods) == 2 and isinstance(mods[0], torch.nn.Linear)
-                and isinstance(mods[1], torch.nn.ReLU) and flat.is_cuda and flat.shape[0] >= self.TC_GEMM_MIN_ROWS
+        if (mods is not None and len(mods) == 2 and isinstance(mods[0], torch.nn.Linear) and isinstance(mods[1], torch.nn.ReLU)
                 and gemm_op.usable(mods[0].in_features, mods[0].out_features)):
-            return gemm_op.linear_tf32x3(flat, mods[0].weight, mods[0].bias, relu=True)
-        return head(flat)
+            return mods
+        return None
+
+    def _head_fuses_input_relu(self, n_rows):
+        if os.environ.get("RLPYT_B200_FUSE_RELU_BWD", "1") != "1":      # cross-check switch (tests)
+            return False
+        return self._head_mods() is not None and n_rows >= self.TC_GEMM_MIN_ROWS and gemm_op.fuses_input_relu(n_rows)
+
+    def _head(self, flat, input_is_relu_output=False):
+        """Linear(conv_out -> fc) + ReLU: the fp32-accurate tcgen05 GEMM for minibatch-sized inputs."""
+        mods = self._head_mods()
+        if mods is not None and flat.is_cuda and flat.shape[0] >= self.TC_GEMM_MIN_ROWS:
+            return gemm_op.linear_tf32x3(flat, mods[0].weight, mods[0].bias, relu=True, input_is_relu_output=input_is_relu_output)
+        assert not input_is_relu_output
+        return self.conv.head(flat)
 
     @torch.no_grad()
     def forward_step(self, image, prev_action, prev_reward, distribution, uniform=None):
