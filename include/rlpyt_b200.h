@@ -317,6 +317,12 @@ int64_t rl_conv1_u8_wgrad_i8_scratch_bytes(void);
 int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
                          float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
                          void* stream);
+/* The same with the per-channel bound max |grad_out[:, oc]| (16 floats in device memory, an upper bound is enough)
+ * supplied by the caller - rl_conv2_dgrad_s2d_absmax produces it in its epilogue - instead of a separate pass over
+ * grad_out. */
+int rl_conv1_u8_wgrad_i8_scaled(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                                const float* chan_absmax, float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W,
+                                void* scratch, void* stream);
 
 /* ------------------------------------------------------------------ second conv layer without im2col expansion
  * Same contracts as rl_conv2_forward_tc / rl_conv2_dgrad_tc (Conv2d(16->32, k4, s2, p1), fp32 NCHW;
@@ -330,6 +336,10 @@ int rl_conv2_forward_s2d(const float* x, const float* weight, const float* bias,
                          int IH, int IW, int relu, void* stream);
 int rl_conv2_dgrad_s2d(const float* grad_out_masked, const float* weight, float* grad_x, int64_t N, int C, int IH,
                        int IW, void* stream);
+/* rl_conv2_dgrad_s2d that also writes chan_absmax[16] = max |grad_x[:, c]| per input channel (device floats), for the
+ * first layer's rl_conv1_u8_wgrad_i8_scaled. */
+int rl_conv2_dgrad_s2d_absmax(const float* grad_out_masked, const float* weight, float* grad_x, float* chan_absmax, int64_t N,
+                              int C, int IH, int IW, void* stream);
 /* Weight / bias gradient in the same cell space (grad_out already ReLU-masked): both operands MN-major with
  * K = cells, M = 64 accumulators per tap promoted to fp32 registers per image, per-CTA partials reduced in a
  * fixed order.  grad_weight [32,16,4,4], grad_bias [32] (nullable); scratch: rl_conv2_wgrad_s2d_scratch_bytes(). */

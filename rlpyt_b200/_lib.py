@@ -73,9 +73,11 @@ SIGNATURES = {
     "rl_conv1_u8_forward_i8_stream": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "rl_conv1_u8_wgrad_i8_scratch_bytes": (c_int64, []),
     "rl_conv1_u8_wgrad_i8": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
+    "rl_conv1_u8_wgrad_i8_scaled": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
     "rl_conv2_s2d_supported": (c_int, [c_int, c_int, c_int]),
     "rl_conv2_forward_s2d": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "rl_conv2_dgrad_s2d": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "rl_conv2_dgrad_s2d_absmax": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P]),
     "rl_categorical_sample_f32": (c_int, [P, P, P, P, P, c_int64, c_int, P]),
     "rl_conv2_wgrad_s2d_scratch_bytes": (c_int64, []),
     "rl_conv2_wgrad_s2d": (c_int, [P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),

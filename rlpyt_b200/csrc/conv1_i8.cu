@@ -59,9 +59,9 @@ int64_t rl_conv1_u8_wgrad_i8_scratch_bytes(void) {
     return static_cast<int64_t>(wg::scratch_bytes(sms));
 }
 
-int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+static int wgrad_i8_impl(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
                          float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
-                         void* stream) {
+                         void* stream, const float* chan_absmax) {
     RL_REQUIRE(obs && grad_out && grad_weight && scratch, RL_EINVAL, "rl_conv1_u8_wgrad_i8: null pointer");
     RL_REQUIRE(N >= 0 && geom_ok(C, H, W), RL_EINVAL,
                "rl_conv1_u8_wgrad_i8: needs C=4, H %% 4 == 0, W %% 4 == 0, W <= 128 (got C=%d H=%d W=%d)", C, H, W);
@@ -79,12 +79,25 @@ int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* o
     }
     const Geom g = make_geom(N, H, W);
     RL_REQUIRE(wg::smem_ok(g), RL_EINVAL, "rl_conv1_u8_wgrad_i8: frame too large for the shared-memory rings (%dx%d)", H, W);
-    const cudaError_t e = wg::launch_wgrad(obs, rows, out, grad_out, grad_weight, grad_bias, g, sms, scratch, st);
+    const cudaError_t e = wg::launch_wgrad(obs, rows, out, grad_out, grad_weight, grad_bias, g, sms, scratch, st, chan_absmax);
     if (e != cudaSuccess) {
         rl::set_error("rl_conv1_u8_wgrad_i8: %s", cudaGetErrorString(e));
         return static_cast<int>(e);
     }
     return RL_OK;
+}
+
+int rl_conv1_u8_wgrad_i8(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                         float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W, void* scratch,
+                         void* stream) {
+    return wgrad_i8_impl(obs, rows, out, grad_out, grad_weight, grad_bias, N, C, H, W, scratch, stream, nullptr);
+}
+
+int rl_conv1_u8_wgrad_i8_scaled(const uint8_t* obs, const int64_t* rows, const float* out, const float* grad_out,
+                                const float* chan_absmax, float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W,
+                                void* scratch, void* stream) {
+    RL_REQUIRE(chan_absmax != nullptr, RL_EINVAL, "rl_conv1_u8_wgrad_i8_scaled: null chan_absmax");
+    return wgrad_i8_impl(obs, rows, out, grad_out, grad_weight, grad_bias, N, C, H, W, scratch, stream, chan_absmax);
 }
 
 }  // extern "C"

@@ -701,7 +701,7 @@ inline bool smem_ok(const Geom& g) {
 
 // scratch: [16 floats gmax | partial ints | partial bias]; out may be null (grad_out already masked)
 inline cudaError_t launch_wgrad(const uint8_t* X, const int64_t* rows, const float* Out, const float* G, float* dW, float* db,
-                                const Geom& g, int sms, void* scratch, cudaStream_t st) {
+                                const Geom& g, int sms, void* scratch, cudaStream_t st, const float* chan_absmax = nullptr) {
     const int P = g.OH * g.OW;
     const SmemLayout L(g.raw_stage_bytes, static_cast<uint32_t>(kOC * P * 4));
     static uint32_t attr_bytes = 0;
@@ -714,9 +714,13 @@ inline cudaError_t launch_wgrad(const uint8_t* X, const int64_t* rows, const flo
     int* partial = reinterpret_cast<int*>(static_cast<uint8_t*>(scratch) + 64);
     const int grid = g.n_img < sms ? g.n_img : sms;
     float* partial_bias = reinterpret_cast<float*>(partial + static_cast<size_t>(grid) * 2 * kRows * kN);
-    cudaError_t e = cudaMemsetAsync(gmax, 0, 64, st);
-    if (e != cudaSuccess) return e;
-    absmax_kernel<<<sms * 8, 256, 0, st>>>(G, static_cast<int64_t>(g.n_img) * kOC, P, reinterpret_cast<unsigned int*>(gmax));
+    if (chan_absmax != nullptr) {    // the producer of G already knows max |G[:, oc]| (conv2's input-gradient epilogue)
+        gmax = const_cast<float*>(chan_absmax);
+    } else {
+        cudaError_t e = cudaMemsetAsync(gmax, 0, 64, st);
+        if (e != cudaSuccess) return e;
+        absmax_kernel<<<sms * 8, 256, 0, st>>>(G, static_cast<int64_t>(g.n_img) * kOC, P, reinterpret_cast<unsigned int*>(gmax));
+    }
     conv1_i8_wgrad_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(X, rows, Out, G, gmax, partial, partial_bias, g);
     wgrad_i8_reduce_kernel<<<2 * kRows + 1, 128, 0, st>>>(partial, partial_bias, gmax, grid, dW, db);
     return cudaGetLastError();

@@ -49,6 +49,29 @@ int rl_conv2_dgrad_s2d(const float* grad_out_masked, const float* weight, float*
     return RL_OK;
 }
 
+int rl_conv2_dgrad_s2d_absmax(const float* grad_out_masked, const float* weight, float* grad_x, float* chan_absmax, int64_t N,
+                              int C, int IH, int IW, void* stream) {
+    RL_REQUIRE(grad_out_masked && weight && grad_x && chan_absmax, RL_EINVAL, "rl_conv2_dgrad_s2d_absmax: null pointer");
+    RL_REQUIRE(N >= 0 && N < (int64_t(1) << 31) && geom_ok(C, IH, IW), RL_EINVAL,
+               "rl_conv2_dgrad_s2d_absmax: needs C=16, OW <= 14 (got C=%d %dx%d)", C, IH, IW);
+    const Geom g = make_geom(N, IH, IW);
+    RL_REQUIRE(dg::smem_ok(g), RL_EINVAL, "rl_conv2_dgrad_s2d_absmax: plane too large for the shared-memory stages (%dx%d)", IH, IW);
+    RL_REQUIRE(rl::aligned(grad_out_masked, 16) && rl::aligned(grad_x, 16) && rl::aligned(chan_absmax, 4), RL_EALIGN,
+               "rl_conv2_dgrad_s2d_absmax: gradients must be 16-byte aligned (bulk copies)");
+    int sms = rl::sm_count();
+    if (sms <= 0) sms = 148;
+    if (N == 0) {
+        cudaMemsetAsync(chan_absmax, 0, 16 * sizeof(float), rl::as_stream(stream));
+        return rl::check_launch("rl_conv2_dgrad_s2d_absmax");
+    }
+    const cudaError_t e = dg::launch_dgrad(grad_out_masked, weight, grad_x, g, sms, rl::as_stream(stream), chan_absmax);
+    if (e != cudaSuccess) {
+        rl::set_error("rl_conv2_dgrad_s2d_absmax: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    return RL_OK;
+}
+
 int64_t rl_conv2_wgrad_s2d_scratch_bytes(void) {
     int sms = rl::sm_count();
     if (sms <= 0) sms = 148;

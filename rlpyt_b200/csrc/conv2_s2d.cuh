@@ -326,7 +326,8 @@ __device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, 
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv2_s2d_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ Wg, float* __restrict__ dX, Geom g) {
+conv2_s2d_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ Wg, float* __restrict__ dX, Geom g,
+                       unsigned int* __restrict__ chan_absmax) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int P = g.OH * g.OW;
@@ -466,6 +467,12 @@ conv2_s2d_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ Wg
         const int qw = warp - kEpiWarp0;
         const uint32_t lane_base = static_cast<uint32_t>(qw * 32) << 16;
         const int plane = g.IH * g.IW;
+        // chan_absmax (optional): max |dX[:, c]| per input channel over the whole call, as the bit pattern of a
+        // non-negative float - the scale the first layer's kind::i8 weight gradient quantises this gradient against
+        // (conv1_i8.cuh wg: S_c = 2^e > max |g[:, c]|), produced here for free instead of by a 43 us pass over dX.
+        float cmax[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) cmax[c] = 0.0f;
         uint32_t it = 0;
         for (int i = 0; i < n_local; ++i) {
             const int64_t n = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
@@ -491,9 +498,11 @@ conv2_s2d_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ Wg
                         for (int col = 0; col < 32; ++col) {
                             const int nn = h * 32 + col, c = nn >> 2, dy = (nn >> 1) & 1, dx = nn & 1;
                             const int iy = 2 * Yc - 1 + dy, ix = 2 * Xc - 1 + dx;
-                            if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
-                                sts32u(o_base + static_cast<uint32_t>(c * plane + iy * g.IW + ix) * 4u,
-                                             __float_as_uint(__uint_as_float(r0[col]) + __uint_as_float(r1[col])));
+                            if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
+                                const float v = __uint_as_float(r0[col]) + __uint_as_float(r1[col]);
+                                sts32u(o_base + static_cast<uint32_t>(c * plane + iy * g.IW + ix) * 4u, __float_as_uint(v));
+                                cmax[c] = fmaxf(cmax[c], fabsf(v));
+                            }
                         }
                     }
                 }
@@ -512,6 +521,15 @@ conv2_s2d_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ Wg
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (chan_absmax != nullptr) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                float m = cmax[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0 && m > 0.0f) atomicMax(chan_absmax + c, __float_as_uint(m));
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -523,7 +541,8 @@ inline bool smem_ok(const Geom& g) {
     return SmemLayout(static_cast<uint32_t>(kOC * g.OH * g.OW * 4), g.img_bytes).total <= 232448u;
 }
 
-inline cudaError_t launch_dgrad(const float* G, const float* W, float* dX, const Geom& g, int sms, cudaStream_t st) {
+inline cudaError_t launch_dgrad(const float* G, const float* W, float* dX, const Geom& g, int sms, cudaStream_t st,
+                                float* chan_absmax = nullptr) {
     const SmemLayout L(static_cast<uint32_t>(kOC * g.OH * g.OW * 4), g.img_bytes);
     static uint32_t attr_bytes = 0;
     if (L.total > attr_bytes) {
@@ -532,7 +551,11 @@ inline cudaError_t launch_dgrad(const float* G, const float* W, float* dX, const
         attr_bytes = L.total;
     }
     const int grid = g.n_img < sms ? g.n_img : sms;
-    conv2_s2d_dgrad_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(G, W, dX, g);
+    if (chan_absmax != nullptr) {
+        cudaError_t e = cudaMemsetAsync(chan_absmax, 0, kC * sizeof(float), st);
+        if (e != cudaSuccess) return e;
+    }
+    conv2_s2d_dgrad_kernel<<<static_cast<unsigned>(grid), kThreads, L.total, st>>>(G, W, dX, g, reinterpret_cast<unsigned int*>(chan_absmax));
     return cudaGetLastError();
 }
 

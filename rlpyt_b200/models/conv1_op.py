@@ -50,6 +50,20 @@ def supported(image_shape, conv_layers):
             and len(conv_layers) > 1 and isinstance(conv_layers[1], torch.nn.ReLU))
 
 
+def _producer_absmax(g):
+    """max |g[:, c]| per channel if ``g`` is the very tensor conv2's input-gradient kernel just wrote (it leaves the
+    maxima of its result in ``conv2_op.LAST_DGRAD_ABSMAX``): same live object, same memory.  Anything else - an
+    accumulated or copied gradient, another producer - gets ``None`` and the kernel's own absmax pass."""
+    from rlpyt_b200.models import conv2_op
+    rec = conv2_op.LAST_DGRAD_ABSMAX.pop(str(g.device), None)
+    if rec is None:
+        return None
+    src = rec["ref"]()
+    if src is None or src.data_ptr() != g.data_ptr() or rec["ptr"] != g.data_ptr() or src.shape != g.shape or src._version != g._version:
+        return None
+    return rec["absmax"]
+
+
 class Conv1U8Relu(torch.autograd.Function):
 
     @staticmethod
@@ -83,9 +97,14 @@ class Conv1U8Relu(torch.autograd.Function):
             gb = torch.empty(16, dtype=torch.float32, device=dev)
             g = grad_out.contiguous()
             sc = _scratch(dev, "wgrad_i8", _lib.load().rl_conv1_u8_wgrad_i8_scratch_bytes)
+            absmax = _producer_absmax(g)
             with torch.cuda.device(dev):
-                _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(gw),
-                          _lib.ptr(gb), N, C, H, W, _lib.ptr(sc), _lib.stream(), n_launch=3)
+                if absmax is not None:      # the per-channel bound came with the gradient (conv2's input-gradient epilogue)
+                    _lib.call("rl_conv1_u8_wgrad_i8_scaled", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(absmax),
+                              _lib.ptr(gw), _lib.ptr(gb), N, C, H, W, _lib.ptr(sc), _lib.stream(), n_launch=2)
+                else:
+                    _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(gw),
+                              _lib.ptr(gb), N, C, H, W, _lib.ptr(sc), _lib.stream(), n_launch=3)
             return gw, gb, None, None
         if impl == "tc":
             from rlpyt_b200.models.conv2_op import wgrad_scratch

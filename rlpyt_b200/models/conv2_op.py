@@ -11,6 +11,12 @@ from rlpyt_b200 import _lib
 from rlpyt_b200.models.gemm_op import relu_backward
 
 _SCRATCH = {}
+# max |grad_x[:, c]| per channel of the last input gradient this op produced: {"ref": weakref to that gradient tensor,
+# "absmax": 16 device floats}.  The first layer's kind::i8 weight gradient needs exactly this bound for its gradient
+# operand and finds it here when the tensor it receives IS that gradient (same object alive, same memory) - else it runs
+# its own pass (models/conv1_op.py).
+LAST_DGRAD_ABSMAX = {}
+FUSE_ABSMAX = os.environ.get("RLPYT_B200_FUSE_ABSMAX", "1") == "1"
 WGRAD_IMPL = os.environ.get("RLPYT_B200_CONV_WGRAD", "tc")
 CONV2_IMPL = os.environ.get("RLPYT_B200_CONV2", "s2d")
 _S2D_OK = {}
@@ -66,8 +72,15 @@ class Conv2ReluTC(torch.autograd.Function):
         if ctx.needs_input_grad[0] and s2d_supported(C, IH, IW):
             gx = torch.empty_like(x)
             with torch.cuda.device(x.device):
-                _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx), N, C, IH, IW,
-                          _lib.stream())
+                if FUSE_ABSMAX:
+                    import weakref
+                    absmax = torch.empty(16, dtype=torch.float32, device=x.device)
+                    _lib.call("rl_conv2_dgrad_s2d_absmax", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx),
+                              _lib.ptr(absmax), N, C, IH, IW, _lib.stream())
+                    LAST_DGRAD_ABSMAX[str(x.device)] = dict(ref=weakref.ref(gx), ptr=gx.data_ptr(), absmax=absmax)
+                else:
+                    _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(g), _lib.ptr(weight.detach().contiguous()), _lib.ptr(gx), N, C, IH, IW,
+                              _lib.stream())
         elif ctx.needs_input_grad[0]:
             dev = x.device
             scratch = _SCRATCH.get(str(dev))

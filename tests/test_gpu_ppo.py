@@ -369,3 +369,43 @@ def test_relu_backward_fused_into_fc_input_gradient_is_bit_identical(monkeypatch
     assert all(float(x.abs().max()) > 0 for x in a.values())
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+
+def test_channel_absmax_from_conv2_dgrad_epilogue_is_bit_identical(monkeypatch):
+    """conv2's input-gradient kernel leaves max |grad[:, c]| per channel in device memory (rl_conv2_dgrad_s2d_absmax) and the
+    first layer's kind::i8 weight gradient takes it from there (rl_conv1_u8_wgrad_i8_scaled) instead of running its own
+    absmax pass: the maxima equal torch's, and every parameter gradient of the model is bit-identical with and without
+    the hand-over."""
+    import importlib
+    from rlpyt_b200.models import conv2_op
+    from rlpyt_b200.models.pg.atari_ff_model import AtariFfModel
+    torch.manual_seed(5)
+    model = AtariFfModel((4, 84, 84), 6).cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    obs = torch.randint(0, 256, (1100, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    gp = torch.randn(1100, 6, device="cuda", generator=g)
+    gv = torch.randn(1100, device="cuda", generator=g)
+    seen = {}
+
+    def grads(fused):
+        monkeypatch.setattr(conv2_op, "FUSE_ABSMAX", fused)
+        conv2_op.LAST_DGRAD_ABSMAX.clear()
+        model.zero_grad(set_to_none=True)
+        pi, v = model(obs, None, None)
+        if fused:      # look at what the epilogue produced before the first layer consumes it
+            from rlpyt_b200.models import conv1_op
+            orig = conv1_op._producer_absmax
+
+            def spy(gr):
+                out = orig(gr)
+                seen["absmax"], seen["ref"] = out, gr.abs().amax(dim=(0, 2, 3))
+                return out
+            monkeypatch.setattr(conv1_op, "_producer_absmax", spy)
+        torch.autograd.backward([pi, v], [gp, gv])
+        return {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    a, b = grads(False), grads(True)
+    assert seen["absmax"] is not None and torch.equal(seen["absmax"], seen["ref"])
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
