@@ -356,14 +356,17 @@ def step_kernel_rooflines(N=8192, reps=10):
     sc_w2 = torch.empty(int(lib.rl_conv2_wgrad_s2d_scratch_bytes()) // 4 + 4, device="cuda")
     fa = torch.randn(N, 3200, device="cuda", generator=gen)
     fb = torch.randn(512, 3200, device="cuda", generator=gen)
+    amax1 = g1.abs().amax(dim=(0, 2, 3)).contiguous()        # what rl_conv2_dgrad_s2d_absmax hands to the first layer's weight gradient
+    amax2 = torch.empty(16, device="cuda")
     C, H, W = IMAGE
     P1, P2 = 16 * oh * ow * 4, 32 * oh2 * ow2 * 4
     i8 = bool(lib.rl_conv1_u8_i8_supported(C, H, W))
     s2d = bool(lib.rl_conv2_s2d_supported(16, oh, ow))
     kernels = [
-        (("conv1_i8_wgrad_kernel + absmax + reduce (kind::i8)" if i8 else "conv_wgrad_tc_kernel<Layer1>") + " [N=8192, (4,84,84) u8]",
-         (lambda: _lib.call("rl_conv1_u8_wgrad_i8", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(gw1),
-                            _lib.ptr(gb1), N, C, H, W, _lib.ptr(sc_i8), _lib.stream(), n_launch=3)) if i8 else
+        (("conv1_i8_wgrad_kernel + reduce (kind::i8; channel maxima handed over by conv2's input-gradient epilogue)" if i8
+          else "conv_wgrad_tc_kernel<Layer1>") + " [N=8192, (4,84,84) u8]",
+         (lambda: _lib.call("rl_conv1_u8_wgrad_i8_scaled", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(amax1),
+                            _lib.ptr(gw1), _lib.ptr(gb1), N, C, H, W, _lib.ptr(sc_i8), _lib.stream(), n_launch=2)) if i8 else
          (lambda: _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(o1), _lib.ptr(g1), _lib.ptr(gw1),
                             _lib.ptr(gb1), N, C, H, W, _lib.ptr(sc_tc), _lib.stream(), n_launch=2)),
          N * (C * H * W + 2 * P1), "conv1_wgrad_bytes_per_launch"),
@@ -375,8 +378,9 @@ def step_kernel_rooflines(N=8192, reps=10):
          lambda: _lib.call("rl_conv2_forward_s2d" if s2d else "rl_conv2_forward_tc", _lib.ptr(x2), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(y2),
                            N, 16, oh, ow, 1, _lib.stream()),
          N * (P1 + P2), "conv2_fwd_bytes_per_launch"),
-        (("conv2_s2d_dgrad_kernel" if s2d else "conv_fwd_tc_kernel<Dgrad2>") + " [N=8192]",
-         (lambda: _lib.call("rl_conv2_dgrad_s2d", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.stream())) if s2d else
+        (("conv2_s2d_dgrad_kernel (+ per-channel |gradient| maxima)" if s2d else "conv_fwd_tc_kernel<Dgrad2>") + " [N=8192]",
+         (lambda: _lib.call("rl_conv2_dgrad_s2d_absmax", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), _lib.ptr(amax2), N, 16, oh, ow,
+                            _lib.stream())) if s2d else
          (lambda: _lib.call("rl_conv2_dgrad_tc", _lib.ptr(g2), _lib.ptr(w2), _lib.ptr(gx2), N, 16, oh, ow, _lib.ptr(sc_dg), _lib.stream(),
                             n_launch=2)),
          N * (P1 + P2), "conv2_dgrad_bytes_per_launch"),
@@ -418,7 +422,8 @@ def step_kernel_rooflines(N=8192, reps=10):
         return gemm_op.gemm_ts(fa, fb, gemm_op.split_lo(fb), None, True) if ts_impl else gemm_tn(fa, fb)
 
     def fc_dgrad():
-        return gemm_op.gemm_ts(fg, *gemm_op.transpose_split(fb)) if ts_impl else gemm_tn(fg, gemm_op.transpose2d(fb))
+        # the product path folds the preceding ReLU's backward into this GEMM's epilogue (out_mask = the layer's input)
+        return gemm_op.gemm_ts(fg, *gemm_op.transpose_split(fb), out_mask=fa) if ts_impl else gemm_tn(fg, gemm_op.transpose2d(fb))
 
     def fc_wgrad():
         if ts_impl:
