@@ -422,8 +422,7 @@ def step_kernel_rooflines(N=8192, reps=10):
         return gemm_op.gemm_ts(fa, fb, gemm_op.split_lo(fb), None, True) if ts_impl else gemm_tn(fa, fb)
 
     def fc_dgrad():
-        # the product path folds the preceding ReLU's backward into this GEMM's epilogue (out_mask = the layer's input)
-        return gemm_op.gemm_ts(fg, *gemm_op.transpose_split(fb), out_mask=fa) if ts_impl else gemm_tn(fg, gemm_op.transpose2d(fb))
+        return gemm_op.gemm_ts(fg, *gemm_op.transpose_split(fb)) if ts_impl else gemm_tn(fg, gemm_op.transpose2d(fb))
 
     def fc_wgrad():
         if ts_impl:

@@ -324,6 +324,19 @@ int rl_conv1_u8_wgrad_i8_scaled(const uint8_t* obs, const int64_t* rows, const f
                                 const float* chan_absmax, float* grad_weight, float* grad_bias, int64_t N, int C, int H, int W,
                                 void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ policy + value heads in training
+ * rlpyt/models/pg/atari_ff_model.py:56-61: pi = softmax(h W_pi^T + b_pi), v = h w_v^T + b_v for h [N,F], W_pi [A,F],
+ * w_v [F] (A <= 32) - forward in one kernel, backward (softmax backward, both input gradients summed, both weight and
+ * bias gradients; grad_prob / grad_value nullable = zero) in one kernel + a fixed-order fp64 reduction over CTAs
+ * (F <= 1024; scratch: rl_pg_heads_backward_scratch_bytes(N, F, A) bytes).  Replaces the two torch.nn.Linear + softmax
+ * (five SIMT GEMM / GEMV launches, split-K and bias reductions: the heads are 6 and 1 columns wide). */
+int rl_pg_heads_forward_f32(const float* h, const float* w_pi, const float* b_pi, const float* w_v, const float* b_v,
+                            float* prob, float* value, int64_t N, int F, int A, void* stream);
+int64_t rl_pg_heads_backward_scratch_bytes(int64_t N, int F, int A);
+int rl_pg_heads_backward_f32(const float* h, const float* prob, const float* grad_prob, const float* grad_value,
+                             const float* w_pi, const float* w_v, float* grad_h, float* grad_w_pi, float* grad_b_pi,
+                             float* grad_w_v, float* grad_b_v, int64_t N, int F, int A, void* scratch, void* stream);
+
 /* ------------------------------------------------------------------ second conv layer without im2col expansion
  * Same contracts as rl_conv2_forward_tc / rl_conv2_dgrad_tc (Conv2d(16->32, k4, s2, p1), fp32 NCHW;
  * rlpyt/models/conv2d.py:36-44, rlpyt/models/pg/atari_ff_model.py:31-35): space-to-depth "cell" rows, the four 2x2

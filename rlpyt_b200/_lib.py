@@ -32,6 +32,9 @@ SIGNATURES = {
     "rl_pg_loss_scratch_bytes": (c_int64, [c_int64]),
     "rl_ppo_loss_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float, c_float, P, P, P, P, P]),
     "rl_ppo_loss_devclip_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, P, c_float, c_float, P, P, P, P, P]),
+    "rl_pg_heads_forward_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_int, P]),
+    "rl_pg_heads_backward_scratch_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "rl_pg_heads_backward_f32": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, P, P]),
     "rl_gather_rows": (c_int, [P, P, P, c_int64, c_int64, P]),
     "rl_gather_rows_multi": (c_int, [c_int, P, P, P, P, c_int64, P]),
     "rl_clip_adam_scratch_bytes": (c_int64, [c_int64]),

@@ -10,7 +10,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from rlpyt_b200.models import conv1_op, conv2_op, gemm_op
+from rlpyt_b200.models import conv1_op, conv2_op, gemm_op, heads_op
 from rlpyt_b200.models.conv2d import Conv2dHeadModel
 from rlpyt_b200.utils.gather import HostMappedFrames, LazyRows
 from rlpyt_b200.utils.tensor import infer_leading_dims, restore_leading_dims
@@ -55,8 +55,12 @@ class AtariFfModel(torch.nn.Module):
         else:
             x = layers[2:](x)
         fc_out = self._head(x.view(x.shape[0], -1), input_is_relu_output=fuse)
-        pi = F.softmax(self.pi(fc_out), dim=-1)
-        v = self.value(fc_out).squeeze(-1)
+        if (os.environ.get("RLPYT_B200_FUSED_HEADS", "1") == "1" and isinstance(self.pi, torch.nn.Linear)
+                and isinstance(self.value, torch.nn.Linear) and heads_op.usable(fc_out, self.pi.in_features, self.pi.out_features)):
+            pi, v = heads_op.policy_value_heads(fc_out, self.pi, self.value)      # both heads + softmax: one kernel each way
+        else:
+            pi = F.softmax(self.pi(fc_out), dim=-1)
+            v = self.value(fc_out).squeeze(-1)
         return pi.view(lead_shape + pi.shape[1:]), v.view(lead_shape)
 
     # tiny batches (the single example step at start-up) stay on cuBLAS; from B=64 up the tcgen05 GEMM
@@ -72,7 +76,9 @@ class AtariFfModel(torch.nn.Module):
         return None
 
     def _head_fuses_input_relu(self, n_rows):
-        if os.environ.get("RLPYT_B200_FUSE_RELU_BWD", "1") != "1":      # cross-check switch (tests)
+        # measured on the B200 (profiles/r02_launches_ppo_iter.csv): the masked epilogue's uncoalesced mask reads stall the
+        # GEMM's drain warps - 208 us against 130 us + a 55 us ReLU-backward pass - so the fusion stays opt-in
+        if os.environ.get("RLPYT_B200_FUSE_RELU_BWD", "0") != "1":
             return False
         return self._head_mods() is not None and n_rows >= self.TC_GEMM_MIN_ROWS and gemm_op.fuses_input_relu(n_rows)
 
