@@ -21,44 +21,65 @@ constexpr int kPhThreads = kPhWarps * 32;
 constexpr int kPhMaxA = 32;
 constexpr int kPhMaxCols = 4;                    // feature columns per thread in the backward: F <= 1024
 
+// Forward.  The A + 1 weight rows are staged in shared memory once per CTA ([A + 1][F] floats: 14 KB at A = 6, F = 512);
+// a warp takes rows grid-stride, every lane 4 consecutive features per step (16-byte loads of h, conflict-free 16-byte
+// reads of the weights), AMAX = the action count's bucket so that only A + 1 (not 33) accumulators are live.
+template <int AMAX>
 __global__ void __launch_bounds__(kPhThreads)
 pg_heads_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w_pi, const float* __restrict__ b_pi,
                     const float* __restrict__ w_v, const float* __restrict__ b_v, float* __restrict__ prob,
                     float* __restrict__ value, int64_t N, int F, int A) {
+    extern __shared__ __align__(16) float ws[];              // [A + 1][F]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int A1 = A + 1;
+    for (int i = threadIdx.x; i < A1 * F; i += kPhThreads) ws[i] = i < A * F ? w_pi[i] : w_v[i - A * F];
+    __syncthreads();
+    const bool vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15) == 0);
     for (int64_t row = static_cast<int64_t>(blockIdx.x) * kPhWarps + warp; row < N; row += static_cast<int64_t>(gridDim.x) * kPhWarps) {
         const float* hr = h + row * F;
-        float acc[kPhMaxA + 1];
+        float acc[AMAX + 1];
 #pragma unroll
-        for (int k = 0; k <= kPhMaxA; ++k) acc[k] = 0.0f;
-        for (int f = lane; f < F; f += 32) {
-            const float x = hr[f];
+        for (int k = 0; k <= AMAX; ++k) acc[k] = 0.0f;
+        if (vec) {
+            for (int f = 4 * lane; f < F; f += 128) {
+                const float4 x = *reinterpret_cast<const float4*>(hr + f);
 #pragma unroll
-            for (int k = 0; k < kPhMaxA; ++k)
-                if (k < A) acc[k] = fmaf(x, w_pi[k * F + f], acc[k]);
-            acc[kPhMaxA] = fmaf(x, w_v[f], acc[kPhMaxA]);
+                for (int k = 0; k <= AMAX; ++k)
+                    if (k < A1) {
+                        const float4 w = *reinterpret_cast<const float4*>(ws + k * F + f);
+                        acc[k] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[k]))));
+                    }
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) {
+                const float x = hr[f];
+#pragma unroll
+                for (int k = 0; k <= AMAX; ++k)
+                    if (k < A1) acc[k] = fmaf(x, ws[k * F + f], acc[k]);
+            }
         }
 #pragma unroll
-        for (int k = 0; k <= kPhMaxA; ++k) {
-            if (k < A || k == kPhMaxA) {
+        for (int k = 0; k <= AMAX; ++k)
+            if (k < A1) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
             }
-        }
         if (lane == 0) {
-            float mx = -3.402823466e38f;
+            float mx = -3.402823466e38f, vhead = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kPhMaxA; ++k)
+            for (int k = 0; k <= AMAX; ++k) {
                 if (k < A) { acc[k] += b_pi[k]; mx = fmaxf(mx, acc[k]); }
+                if (k == A) vhead = acc[k];
+            }
             float sum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kPhMaxA; ++k)
+            for (int k = 0; k <= AMAX; ++k)
                 if (k < A) { acc[k] = expf(acc[k] - mx); sum += acc[k]; }
             const float inv = 1.0f / sum;
 #pragma unroll
-            for (int k = 0; k < kPhMaxA; ++k)
+            for (int k = 0; k <= AMAX; ++k)
                 if (k < A) prob[row * A + k] = acc[k] * inv;
-            value[row] = acc[kPhMaxA] + b_v[0];
+            value[row] = vhead + b_v[0];
         }
     }
 }
@@ -151,25 +172,33 @@ pg_heads_bwd_kernel(const float* __restrict__ h, const float* __restrict__ prob,
     if (tid < A1) partial_b[static_cast<int64_t>(blockIdx.x) * A1 + tid] = bsum[tid];
 }
 
-// grad_w_pi [A, F], grad_w_v [F], grad_b_pi [A], grad_b_v [1] = sums over CTAs in fp64, ascending CTA order
+// grad_w_pi [A, F], grad_w_v [F], grad_b_pi [A], grad_b_v [1] = sums over CTAs in fp64 in a FIXED order: one warp per
+// output, lane l adds the partials of CTAs l, l + 32, ... (ascending), then a fixed shuffle tree combines the 32 lanes.
 __global__ void __launch_bounds__(256)
 pg_heads_reduce_kernel(const float* __restrict__ partial_w, const float* __restrict__ partial_b, int n_cta, int F, int A,
                        float* __restrict__ grad_w_pi, float* __restrict__ grad_w_v, float* __restrict__ grad_b_pi,
                        float* __restrict__ grad_b_v) {
     const int A1 = A + 1;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A1 * F) {
-        double s = 0.0;
-        for (int c = 0; c < n_cta; ++c) s += static_cast<double>(partial_w[static_cast<int64_t>(c) * A1 * F + i]);
-        const int a = i / F, f = i - a * F;
-        if (a < A) grad_w_pi[a * F + f] = static_cast<float>(s);
-        else grad_w_v[f] = static_cast<float>(s);
-    } else if (i < A1 * F + A1) {
-        const int a = i - A1 * F;
-        double s = 0.0;
-        for (int c = 0; c < n_cta; ++c) s += static_cast<double>(partial_b[static_cast<int64_t>(c) * A1 + a]);
-        if (a < A) grad_b_pi[a] = static_cast<float>(s);
-        else grad_b_v[0] = static_cast<float>(s);
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // output index, warp-uniform
+    const int n_w = A1 * F;
+    if (i >= n_w + A1) return;
+    const float* src = i < n_w ? partial_w + i : partial_b + (i - n_w);
+    const int64_t stride = i < n_w ? static_cast<int64_t>(n_w) : A1;
+    double s = 0.0;
+    for (int c = lane; c < n_cta; c += 32) s += static_cast<double>(src[static_cast<int64_t>(c) * stride]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (i < n_w) {
+            const int a = i / F, f = i - a * F;
+            if (a < A) grad_w_pi[a * F + f] = static_cast<float>(s);
+            else grad_w_v[f] = static_cast<float>(s);
+        } else {
+            const int a = i - n_w;
+            if (a < A) grad_b_pi[a] = static_cast<float>(s);
+            else grad_b_v[0] = static_cast<float>(s);
+        }
     }
 }
 
@@ -197,9 +226,15 @@ int rl_pg_heads_forward_f32(const float* h, const float* w_pi, const float* b_pi
     if (N == 0) return RL_OK;
     int sms = rl::sm_count();
     if (sms <= 0) sms = 148;
+    RL_REQUIRE(static_cast<size_t>(A + 1) * F * sizeof(float) <= 48 * 1024, RL_EINVAL,
+               "rl_pg_heads_forward_f32: (A + 1) * F floats must fit 48 KB of shared memory (A=%d F=%d)", A, F);
     int64_t grid = (N + rl::kPhWarps - 1) / rl::kPhWarps;
-    if (grid > 8LL * sms) grid = 8LL * sms;
-    rl::pg_heads_fwd_kernel<<<static_cast<unsigned>(grid), rl::kPhThreads, 0, rl::as_stream(stream)>>>(h, w_pi, b_pi, w_v, b_v, prob, value, N, F, A);
+    if (grid > 4LL * sms) grid = 4LL * sms;                  // each CTA stages the weights once, then takes rows grid-stride
+    const size_t smem = static_cast<size_t>(A + 1) * F * sizeof(float);
+    cudaStream_t st = rl::as_stream(stream);
+    if (A <= 8) rl::pg_heads_fwd_kernel<8><<<static_cast<unsigned>(grid), rl::kPhThreads, smem, st>>>(h, w_pi, b_pi, w_v, b_v, prob, value, N, F, A);
+    else if (A <= 16) rl::pg_heads_fwd_kernel<16><<<static_cast<unsigned>(grid), rl::kPhThreads, smem, st>>>(h, w_pi, b_pi, w_v, b_v, prob, value, N, F, A);
+    else rl::pg_heads_fwd_kernel<32><<<static_cast<unsigned>(grid), rl::kPhThreads, smem, st>>>(h, w_pi, b_pi, w_v, b_v, prob, value, N, F, A);
     return rl::check_launch("pg_heads_fwd_kernel");
 }
 
@@ -241,8 +276,8 @@ int rl_pg_heads_backward_f32(const float* h, const float* prob, const float* gra
 #undef RL_PH_LAUNCH
     int rc = rl::check_launch("pg_heads_bwd_kernel");
     if (rc != RL_OK) return rc;
-    const int total = (A + 1) * F + (A + 1);
-    rl::pg_heads_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial_w, partial_b, grid, F, A, grad_w_pi, grad_w_v, grad_b_pi, grad_b_v);
+    const int total = (A + 1) * F + (A + 1);                 // one warp per output
+    rl::pg_heads_reduce_kernel<<<(total + 7) / 8, 256, 0, st>>>(partial_w, partial_b, grid, F, A, grad_w_pi, grad_w_v, grad_b_pi, grad_b_v);
     return rl::check_launch("pg_heads_reduce_kernel");
 }
 

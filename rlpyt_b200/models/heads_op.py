@@ -13,7 +13,7 @@ MAX_F, MAX_A = 1024, 32
 
 def usable(h, n_features, n_actions):
     return (isinstance(h, torch.Tensor) and h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and n_features <= MAX_F
-            and 1 <= n_actions <= MAX_A)
+            and 1 <= n_actions <= MAX_A and (n_actions + 1) * n_features * 4 <= 48 * 1024)
 
 
 class PgHeads(torch.autograd.Function):

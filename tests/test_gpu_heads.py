@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("N,F,A", [(8192, 512, 6), (1, 512, 6), (37, 64, 18), (300, 1000, 32), (1025, 256, 4), (64, 512, 9)])
+@pytest.mark.parametrize("N,F,A", [(8192, 512, 6), (1, 512, 6), (37, 63, 18), (300, 360, 32), (130, 1000, 10), (1025, 256, 4), (64, 512, 9)])
 def test_policy_value_heads_forward_backward_vs_float64(N, F, A):
     from rlpyt_b200.models.heads_op import PgHeads
     g = torch.Generator(device="cuda").manual_seed(N + F + A)
