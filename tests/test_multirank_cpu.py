@@ -93,3 +93,53 @@ def test_reference_arm_runs_on_rank0_only():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def _async_worker(rank, world, port, out):
+    """One rank of a two-rank asynchronous run on gloo: a fast and a slow sampler, stand-in algorithm whose
+    ``optimize_agent`` all-reduces (as the real one's gradient all-reduce does)."""
+    import time
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import test_async_runner_cpu as T
+    from rlpyt_b200.runners.async_rl import AsyncRl
+    from rlpyt_b200.utils.logging import TabularLogger
+
+    class Algo(T.FakeAlgo):
+        def optimize_agent(self, itr, samples=None, sampler_itr=None):
+            t = torch.ones(1)
+            dist.all_reduce(t)                                   # collective: every rank must make the same number of calls
+            assert float(t) == world
+            return super().optimize_agent(itr, samples, sampler_itr)
+
+    class Agent(T.FakeAgent):
+        device = torch.device("cpu")
+
+        def data_parallel(self):
+            self.dp = True
+
+    sampler = T.FakeSampler(step_s=0.001 if rank == 0 else 0.004)   # rank 1 samples four times slower
+    algo = Algo(min_steps_learn=0)
+    runner = AsyncRl(algo=algo, agent=Agent(), sampler=sampler, n_steps=32 * 24, affinity=dict(cuda_idx=None), seed=1,
+                     log_interval_steps=32 * 8, logger=TabularLogger(quiet=True))
+    runner.throttle_wait = 0.002
+    n_opt = runner.train()
+    out[rank] = dict(n_opt=n_opt, calls=len(algo.calls), world=runner.world_size, sampler_itrs=len(sampler.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_runner_ranks_agree_on_every_optimizer_iteration():
+    """``AsyncRl`` under two ranks with unequal sampler speeds: the optimizer loops stay in lock-step (one tiny all-reduce
+    of ready / quit flags before every iteration, the reference's ``opt_throttle`` barrier, async_rl.py:110-111) - a rank
+    never enters the collective inside ``optimize_agent`` alone, and both stop together when the first sampler is done."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_async_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0]["world"] == out[1]["world"] == 2
+    assert out[0]["n_opt"] == out[1]["n_opt"] == out[0]["calls"] == out[1]["calls"] > 0
+    assert out[0]["sampler_itrs"] == 24                       # the fast rank finished its run; the slow one was cut short with it
