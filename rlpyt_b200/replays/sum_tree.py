@@ -129,9 +129,9 @@ class SumTree:
             return self._sample_unique(n, u_np)
         u = torch.as_tensor(np.asarray(u_np, dtype=np.float64) if not isinstance(u_np, torch.Tensor) else u_np,
                             dtype=torch.float64).to(self.device, non_blocking=True)
-        idx = torch.empty(n, dtype=torch.int64, device=self.device)
-        T_idxs, B_idxs = torch.empty_like(idx), torch.empty_like(idx)
-        pri = torch.empty(n, dtype=torch.float64, device=self.device)
+        arena = torch.empty(4 * n, dtype=torch.int64, device=self.device)       # one allocation for the four outputs
+        idx, T_idxs, B_idxs = arena[:n], arena[n:2 * n], arena[2 * n:3 * n]
+        pri = arena[3 * n:].view(torch.float64)
         with torch.cuda.device(self.device):
             _lib.call("rl_sumtree_find_f64", _lib.ptr(self.tree), self.tree_levels, _lib.ptr(u), int(n), self.B,
                       _lib.ptr(idx), _lib.ptr(T_idxs), _lib.ptr(B_idxs), _lib.ptr(pri), None, _lib.stream())
