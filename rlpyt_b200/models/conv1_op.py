@@ -12,6 +12,7 @@ import os
 import torch
 
 from rlpyt_b200 import _lib
+from rlpyt_b200.algos.optim import grad_destination
 
 _SCRATCH = {}
 FORWARD_IMPL = os.environ.get("RLPYT_B200_CONV1_FWD", "i8")
@@ -80,6 +81,7 @@ class Conv1U8Relu(torch.autograd.Function):
         with torch.cuda.device(obs.device):
             _lib.call(fn, _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), N, C, H, W, 1, _lib.stream())
         ctx.obs, ctx.rows = obs, rows
+        ctx.params = (weight, bias)                          # for grad_destination (the flat gradient buffer's slots)
         ctx.save_for_backward(out)
         ctx.mark_non_differentiable()
         return out
@@ -93,8 +95,7 @@ class Conv1U8Relu(torch.autograd.Function):
         dev = obs.device
         impl = _impl(WGRAD_IMPL, C, H, W, N)
         if impl == "i8":
-            gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
-            gb = torch.empty(16, dtype=torch.float32, device=dev)
+            gw, gb = grad_destination(ctx.params[0]), grad_destination(ctx.params[1])
             g = grad_out.contiguous()
             sc = _scratch(dev, "wgrad_i8", _lib.load().rl_conv1_u8_wgrad_i8_scratch_bytes)
             absmax = _producer_absmax(g)
@@ -108,8 +109,7 @@ class Conv1U8Relu(torch.autograd.Function):
             return gw, gb, None, None
         if impl == "tc":
             from rlpyt_b200.models.conv2_op import wgrad_scratch
-            gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
-            gb = torch.empty(16, dtype=torch.float32, device=dev)
+            gw, gb = grad_destination(ctx.params[0]), grad_destination(ctx.params[1])
             g = grad_out.contiguous()
             with torch.cuda.device(dev):
                 _lib.call("rl_conv1_u8_wgrad_tc", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g),
@@ -122,8 +122,7 @@ class Conv1U8Relu(torch.autograd.Function):
             nbytes = int(_lib.load().rl_conv1_u8_wgrad_scratch_bytes())
             scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
             _SCRATCH[key] = scratch
-        gw = torch.empty((16, 4, 8, 8), dtype=torch.float32, device=dev)
-        gb = torch.empty(16, dtype=torch.float32, device=dev)
+        gw, gb = grad_destination(ctx.params[0]), grad_destination(ctx.params[1])
         g = grad_out.contiguous()
         with torch.cuda.device(dev):
             _lib.call("rl_conv1_u8_wgrad", _lib.ptr(obs), _lib.ptr(rows), _lib.ptr(out), _lib.ptr(g), _lib.ptr(gw),

@@ -8,6 +8,7 @@ import os
 import torch
 
 from rlpyt_b200 import _lib
+from rlpyt_b200.algos.optim import grad_destination
 from rlpyt_b200.models.gemm_op import relu_backward
 
 _SCRATCH = {}
@@ -52,6 +53,7 @@ class Conv2ReluTC(torch.autograd.Function):
         input-gradient GEMM zeroes its result where this output is <= 0): ``backward`` must not do it a second time."""
         _lib.require_cuda(x, weight, bias)
         ctx.grad_is_masked = bool(grad_is_masked)
+        ctx.params = (weight, bias)
         x = x.contiguous()
         N, C, IH, IW = x.shape
         OH, OW = (IH - 2) // 2 + 1, (IW - 2) // 2 + 1
@@ -95,8 +97,7 @@ class Conv2ReluTC(torch.autograd.Function):
         if ((ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc" and s2d_supported(C, IH, IW)
                 and ((IH + 2 - 4) // 2 + 2) * ((IW + 2 - 4) // 2 + 2) <= 128):
             # one 128-cell tile per image (20x20 planes): both operands MN-major, K = cells (csrc/conv2_s2d.cuh wg2)
-            gw = torch.empty_like(weight)
-            gb = torch.empty(32, dtype=torch.float32, device=x.device)
+            gw, gb = grad_destination(ctx.params[0]), grad_destination(ctx.params[1])
             sc = _SCRATCH.get(("wgrad_s2d", str(x.device)))
             if sc is None:
                 sc = torch.empty(int(_lib.load().rl_conv2_wgrad_s2d_scratch_bytes()) // 4 + 4, dtype=torch.float32, device=x.device)
@@ -105,8 +106,7 @@ class Conv2ReluTC(torch.autograd.Function):
                 _lib.call("rl_conv2_wgrad_s2d", _lib.ptr(x), _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gb), N, C, IH, IW, _lib.ptr(sc),
                           _lib.stream(), n_launch=2)
         elif (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and WGRAD_IMPL == "tc":
-            gw = torch.empty_like(weight)
-            gb = torch.empty(32, dtype=torch.float32, device=x.device)
+            gw, gb = grad_destination(ctx.params[0]), grad_destination(ctx.params[1])
             with torch.cuda.device(x.device):
                 _lib.call("rl_conv2_wgrad_tc", _lib.ptr(x), None, _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gb),
                           N, C, IH, IW, _lib.ptr(wgrad_scratch(x.device)), _lib.stream(), n_launch=2)

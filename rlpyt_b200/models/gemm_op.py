@@ -11,6 +11,7 @@ import os
 import torch
 
 from rlpyt_b200 import _lib
+from rlpyt_b200.algos.optim import grad_destination
 
 _WS = {}  # split-K workspaces, keyed by (device, bytes)
 GEMM_IMPL = os.environ.get("RLPYT_B200_GEMM_IMPL", "ts")
@@ -50,7 +51,7 @@ def transpose_split(x):
     return dst, lo
 
 
-def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False, out_mask=None):
+def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False, out_mask=None, out=None):
     """a @ b^T (+bias) (+relu).  a: [M,K], or with ``a_mmajor`` the [K,M] matrix a^T; b, b_lo: [N,K];
     result [M,N], or with ``c_trans`` its transpose [N,M].  ``out_mask`` [M,N]: result kept where ``out_mask > 0``, zero
     elsewhere (a preceding ReLU's backward folded into the epilogue; plain form only)."""
@@ -59,7 +60,10 @@ def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False, ou
     (K, M) = a.shape if a_mmajor else a.shape[::-1]
     N = b.shape[0]
     assert b.shape == (N, K) and b_lo.shape == (N, K) and a.dtype == b.dtype == b_lo.dtype == torch.float32
-    out = torch.empty((N, M) if c_trans else (M, N), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((N, M) if c_trans else (M, N), dtype=torch.float32, device=a.device)
+    else:
+        assert tuple(out.shape) == ((N, M) if c_trans else (M, N)) and out.is_contiguous() and out.dtype == torch.float32
     ws = _workspace(a.device, int(_lib.load().rl_gemm_ts_workspace_bytes(M, N, K)))
     if out_mask is not None:
         assert not (a_mmajor or c_trans or relu) and bias is None and tuple(out_mask.shape) == (M, N) and out_mask.is_contiguous()
@@ -73,14 +77,17 @@ def gemm_ts(a, b, b_lo, bias=None, relu=False, a_mmajor=False, c_trans=False, ou
     return out
 
 
-def gemm_tn(a, b, bias=None, relu=False):
+def gemm_tn(a, b, bias=None, relu=False, out=None):
     """a [M,K] @ b[N,K]^T (+bias) (+relu) -> [M,N]; fp32 CUDA, K % 4 == 0."""
     _lib.require_cuda(a, b, bias)
     a, b = a.contiguous(), b.contiguous()
     M, K = a.shape
     N = b.shape[0]
     assert b.shape[1] == K and a.dtype == torch.float32 and b.dtype == torch.float32
-    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    else:
+        assert tuple(out.shape) == (M, N) and out.is_contiguous() and out.dtype == torch.float32
     ws = _workspace(a.device, int(_lib.load().rl_gemm_tf32x3_workspace_bytes(M, N, K)))
     with torch.cuda.device(a.device):
         _lib.call("rl_gemm_tf32x3_f32", _lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), M, N, K,
@@ -134,6 +141,7 @@ class LinearTf32x3(torch.autograd.Function):
             y = gemm_tn(x.detach(), weight.detach(), b, relu)
         ctx.relu = relu
         ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)                          # for grad_destination (the flat gradient buffer's slots)
         ctx.save_for_backward(x, weight, y if relu else None)
         return y
 
@@ -158,11 +166,11 @@ class LinearTf32x3(torch.autograd.Function):
             elif ts:
                 # gw^T [K,N] = x^T [K,M] gy [M,N]: x is read as it lies (the [M,K] matrix is x^T's "M-major" form),
                 # the result is stored transposed, only the small operand gy is transposed (+ split)
-                gw = gemm_ts(x.detach(), *transpose_split(gy), a_mmajor=True, c_trans=True)
+                gw = gemm_ts(x.detach(), *transpose_split(gy), a_mmajor=True, c_trans=True, out=grad_destination(ctx.params[0]))
             else:
-                gw = gemm_tn(transpose2d(gy), transpose2d(x.detach()))   # [N,M] x [K,M]^T
+                gw = gemm_tn(transpose2d(gy), transpose2d(x.detach()), out=grad_destination(ctx.params[0]))   # [N,M] x [K,M]^T
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            gb = torch.sum(gy, 0, out=grad_destination(ctx.params[1]))
         return gx, gw, gb, None, None
 
 

@@ -6,6 +6,7 @@ kernel and the backward one kernel + a small fixed-order reduction, reading ``h`
 import torch
 
 from rlpyt_b200 import _lib
+from rlpyt_b200.algos.optim import grad_destination
 
 _SCRATCH = {}
 MAX_F, MAX_A = 1024, 32
@@ -32,6 +33,7 @@ class PgHeads(torch.autograd.Function):
             _lib.call("rl_pg_heads_forward_f32", _lib.ptr(h.detach()), _lib.ptr(wp), _lib.ptr(bp), _lib.ptr(wv), _lib.ptr(bv),
                       _lib.ptr(pi), _lib.ptr(v), N, F, A, _lib.stream())
         ctx.save_for_backward(h, w_pi, w_v, pi)
+        ctx.params = (w_pi, b_pi, w_v, b_v)
         return pi, v
 
     @staticmethod
@@ -43,8 +45,7 @@ class PgHeads(torch.autograd.Function):
         g_pi = None if g_pi is None else g_pi.contiguous()
         g_v = None if g_v is None else g_v.contiguous()
         gh = torch.empty_like(h)
-        gwp, gbp = torch.empty_like(w_pi), torch.empty(A, dtype=torch.float32, device=dev)
-        gwv, gbv = torch.empty_like(w_v), torch.empty(1, dtype=torch.float32, device=dev)
+        gwp, gbp, gwv, gbv = (grad_destination(p) for p in ctx.params)     # the parameters' slots of the flat gradient buffer
         nbytes = int(_lib.load().rl_pg_heads_backward_scratch_bytes(N, F, A))
         key = (str(dev), nbytes)
         sc = _SCRATCH.get(key)

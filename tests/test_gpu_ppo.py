@@ -409,3 +409,49 @@ def test_channel_absmax_from_conv2_dgrad_epilogue_is_bit_identical(monkeypatch):
     assert seen["absmax"] is not None and torch.equal(seen["absmax"], seen["ref"])
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_direct_gradient_writes_into_the_flat_buffer(monkeypatch):
+    """With ``FlatAdam`` the hand-written backward kernels write each parameter gradient straight into its slot of the flat
+    gradient buffer (algos/optim.py ``grad_destination``) and autograd adopts the slot view as ``.grad`` - no add kernel per
+    parameter.  Checked: (i) every ``.grad`` of the AtariFf network IS its slot after backward; (ii) the flat buffer equals,
+    bit for bit, the one produced by accumulating into attached ``.grad`` views; (iii) a network used TWICE in one graph
+    still accumulates both contributions; (iv) a gradient that arrives some other way is collected into its slot."""
+    from rlpyt_b200.algos.optim import FlatAdam
+    from rlpyt_b200.models.pg.atari_ff_model import AtariFfModel
+    g = torch.Generator(device="cuda").manual_seed(4)
+    obs = torch.randint(0, 256, (1200, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    obs2 = torch.randint(0, 256, (1200, 4, 84, 84), dtype=torch.uint8, device="cuda", generator=g)
+    gp, gv = torch.randn(1200, 6, device="cuda", generator=g), torch.randn(1200, device="cuda", generator=g)
+
+    def run(direct, twice):
+        torch.manual_seed(9)
+        model = AtariFfModel((4, 84, 84), 6).cuda()
+        opt = FlatAdam(model.parameters(), lr=1e-3)
+        opt.direct_grads = direct
+        opt.zero_grad()
+        pi, v = model(obs, None, None)
+        if twice:
+            pi2, v2 = model(obs2, None, None)
+            pi, v = pi + pi2, v + v2
+        torch.autograd.backward([pi, v], [gp, gv])
+        base = opt.flat_grad.data_ptr()
+        in_slot = [p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(opt.param_groups[0]["params"], opt._offsets)]
+        if direct:
+            opt._collect_grads()
+        return opt.flat_grad.clone(), in_slot, opt, model
+
+    ref, _, _, _ = run(False, False)
+    got, in_slot, opt, model = run(True, False)
+    assert all(in_slot)                                              # (i): adopted, not copied
+    assert torch.equal(ref, got)                                     # (ii)
+    ref2, _, _, _ = run(False, True)
+    got2, in_slot2, _, _ = run(True, True)
+    assert torch.allclose(ref2, got2, rtol=1e-6, atol=1e-7) and float(ref2.abs().max()) > 0      # (iii): a + b vs b + a per element
+    # (iv) a foreign gradient
+    opt.zero_grad()
+    p0 = opt.param_groups[0]["params"][0]
+    p0.grad = torch.full_like(p0, 3.0)
+    opt._collect_grads()
+    off = opt._offsets[0]
+    assert float(opt.flat_grad[off:off + p0.numel()].min()) == 3.0 and p0.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * off
