@@ -79,15 +79,15 @@ class FlatAdam(torch.optim.Optimizer):
 
     def _collect_grads(self):
         """Make the flat buffer hold every gradient: a ``.grad`` that is not the parameter's slot (torch-native layers,
-        accumulated or cloned gradients) is copied into it and re-linked; a missing one leaves the slot zero."""
+        accumulated or cloned gradients) is copied into it; a missing one leaves the slot zero.  The foreign tensor
+        STAYS attached: when the backward is a replayed CUDA graph it is the graph's own buffer, rewritten by every
+        replay without any host code running - it has to be collected again each time."""
         base = self.flat_grad.data_ptr()
         for p, off in zip(self.param_groups[0]["params"], self._offsets):
             g = p.grad
             if g is None or g.data_ptr() == base + 4 * off:
                 continue
-            slot = self.flat_grad[off:off + p.numel()].view(p.shape)
-            slot.copy_(g)
-            p.grad = slot
+            self.flat_grad[off:off + p.numel()].view(p.shape).copy_(g)
 
     def set_world_size(self, world_size):
         self.world_size = int(world_size)

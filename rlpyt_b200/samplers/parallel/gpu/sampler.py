@@ -67,6 +67,7 @@ def sampling_process(common_kwargs, worker_kwargs):
         traj_infos, completed = collector.collect_batch(traj_infos, ctrl.itr.value)
         for info in completed:
             c.traj_infos_queue.put(info)
+        c.traj_infos_queue.put(None)                         # end of this worker's batch: the master drains up to one sentinel per worker
         ctrl.barrier_out.wait()
     for env in envs:
         env.close()
@@ -190,7 +191,10 @@ class GpuSampler(BaseSampler):
         self.ctrl.barrier_in.wait()
         self.serve_actions(itr)
         self.ctrl.barrier_out.wait()
-        traj_infos = drain_queue(self.traj_infos_queue)
+        # one sentinel per worker marks the end of its puts for this batch: every trajectory that ended in the batch is
+        # returned WITH the batch (the reference's non-blocking drain, parallel/base.py:69, can miss an item whose
+        # queue feeder thread has not pushed it yet and report it one batch late)
+        traj_infos = drain_queue(self.traj_infos_queue, n_sentinel=self.n_worker)
         return self.samples, traj_infos
 
     def evaluate_agent(self, itr):
