@@ -171,9 +171,21 @@ class PPO(PolicyGradientAlgo):
                               graph=torch.cuda.CUDAGraph(), keep=(obs_f, small))
         torch.cuda.synchronize(dev)
         n0 = _lib.launch_count
-        with torch.cuda.graph(mbg.graph):
+        try:
+            with torch.cuda.graph(mbg.graph):
+                self.optimizer.zero_grad()
+                mbg.sc = self._minibatch_forward_backward(obs_f, small, has_valid, mbg.rows, lazy_obs, mbg.clip)
+        except RuntimeError as e:
+            # an invalidated capture (a CUDA call from outside the body, a library allocating on first use) has executed
+            # nothing on the device: drop what the host side of the body attached and issue minibatches eagerly from now on
+            import warnings
+            warnings.warn(f"rlpyt_b200: CUDA-graph capture of the PPO minibatch failed ({str(e).splitlines()[0][:120]}); "
+                          "minibatches are issued eagerly from now on")
+            _lib.launch_count = n0
+            self._mb_graphs = None
+            torch.cuda.synchronize(dev)
             self.optimizer.zero_grad()
-            mbg.sc = self._minibatch_forward_backward(obs_f, small, has_valid, mbg.rows, lazy_obs, mbg.clip)
+            return None
         mbg.n_launch, _lib.launch_count = _lib.launch_count - n0, n0   # capturing launched nothing
         graphs[key] = mbg
         return mbg

@@ -155,10 +155,23 @@ class DeviceRollout:
         if g is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
-            # "thread_local": in the asynchronous runner other threads of this process keep issuing CUDA calls
-            # (synchronisations, allocations) on their own streams while this thread captures
-            with torch.cuda.graph(g, stream=self.side_stream, capture_error_mode=self.capture_error_mode):
+            try:
+                # "thread_local": in the asynchronous runner other threads of this process keep issuing CUDA calls
+                # (synchronisations, allocations) on their own streams while this thread captures
+                with torch.cuda.graph(g, stream=self.side_stream, capture_error_mode=self.capture_error_mode):
+                    body()
+            except RuntimeError as e:
+                # A capture can be invalidated from outside the body (another thread's or a finalizer's CUDA call in
+                # "global" mode, a library that allocates on first use): nothing of the body has executed on the
+                # device, so the step is simply issued eagerly - and stays eager for this engine.
+                import warnings
+                warnings.warn(f"rlpyt_b200: CUDA-graph capture of the sampler step failed ({str(e).splitlines()[0][:120]}); "
+                              "this sampler steps eagerly from now on")
+                self.use_graphs = False
+                self._graphs.clear()
+                torch.cuda.synchronize(self.device)
                 body()
+                return
             self._graphs[key] = g
         g.replay()
 
