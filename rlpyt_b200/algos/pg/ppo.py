@@ -171,6 +171,7 @@ class PPO(PolicyGradientAlgo):
                               graph=torch.cuda.CUDAGraph(), keep=(obs_f, small))
         torch.cuda.synchronize(dev)
         n0 = _lib.launch_count
+        issuing = torch.cuda.current_stream(dev)
         try:
             with torch.cuda.graph(mbg.graph):
                 self.optimizer.zero_grad()
@@ -183,6 +184,7 @@ class PPO(PolicyGradientAlgo):
                           "minibatches are issued eagerly from now on")
             _lib.launch_count = n0
             self._mb_graphs = None
+            torch.cuda.set_stream(issuing)                   # torch.cuda.graph.__exit__ raised before it restored the stream
             torch.cuda.synchronize(dev)
             self.optimizer.zero_grad()
             return None

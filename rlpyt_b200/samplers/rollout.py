@@ -155,6 +155,7 @@ class DeviceRollout:
         if g is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.device)
+            issuing = torch.cuda.current_stream(self.device)
             try:
                 # "thread_local": in the asynchronous runner other threads of this process keep issuing CUDA calls
                 # (synchronisations, allocations) on their own streams while this thread captures
@@ -169,6 +170,7 @@ class DeviceRollout:
                               "this sampler steps eagerly from now on")
                 self.use_graphs = False
                 self._graphs.clear()
+                torch.cuda.set_stream(issuing)               # torch.cuda.graph.__exit__ raised before it restored the stream
                 torch.cuda.synchronize(self.device)
                 body()
                 return
