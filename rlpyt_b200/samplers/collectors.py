@@ -9,7 +9,7 @@ the next observation, reward and done into the step buffer and ``env_info`` into
 """
 import numpy as np
 
-from rlpyt_b200._lib import host_stream_copy
+from rlpyt_b200._lib import host_stream_copy, host_stream_copy_ptr, load as _load_lib
 
 
 class DecorrelatingStartCollector:
@@ -68,6 +68,9 @@ class GpuResetCollector(DecorrelatingStartCollector):
         envs = self.envs
         n = len(envs)
         obs_rows = [step.observation[b] for b in range(n)]
+        _load_lib()                                              # host_stream_copy_ptr calls the library directly
+        row_ptrs = [row.ctypes.data for row in obs_rows] if step.observation[0].flags["C_CONTIGUOUS"] else None
+        row_nbytes, row_dtype = obs_rows[0].nbytes, obs_rows[0].dtype
         info_np = self.env_info_np
         info_fields = getattr(info_np, "_fields", None)
         if info_fields is not None and not all(isinstance(getattr(info_np, f), np.ndarray) for f in info_fields):
@@ -87,7 +90,9 @@ class GpuResetCollector(DecorrelatingStartCollector):
                     completed.append(traj_infos[b].terminate(o))
                     traj_infos[b] = self.TrajInfoCls()
                     o = env.reset()
-                host_stream_copy(obs_rows[b], o)  # non-temporal: keep the DMA source out of this core's L2
+                # non-temporal copy: keeps the DMA source out of this core's L2 (row address precomputed)
+                if row_ptrs is None or not host_stream_copy_ptr(row_ptrs[b], row_nbytes, row_dtype, o):
+                    host_stream_copy(obs_rows[b], o)
                 rewards[b], dones[b], infos[b] = r, d, env_info
             step.reward[:] = rewards
             step.done[:] = dones
