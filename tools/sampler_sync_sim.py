@@ -44,9 +44,30 @@ class FakeRollout:
         self.step_np, self.gpu_s = step_np, gpu_us * 1e-6
         self.rng = np.random.default_rng(0)
 
-    def step(self, t, zero_inputs_on_done, blank_done_rows=False):
+    side_stream = None
+
+    def step(self, t, zero_inputs_on_done, blank_done_rows=False, obs_done=False):
         end = time.perf_counter() + self.gpu_s
         while time.perf_counter() < end:      # the master thread is busy in the driver for this long
+            pass
+        self.step_np.action[:] = self.rng.integers(0, A, len(self.step_np.action))
+
+    # the alternating master's surface: upload and act issued separately, completion polled or waited for.  The device
+    # phase is modelled as a deadline: H2D 45 % of the half step, agent.step the rest, strictly one after the other.
+    def upload_worker_rows(self, k, i):
+        pass
+
+    def upload_async(self, k, zero_inputs_on_done, obs_done=False):
+        self._ready_at = max(getattr(self, "_ready_at", 0.0), time.perf_counter()) + 0.45 * self.gpu_s
+
+    def act_async(self, k, blank_done_rows=False):
+        self._ready_at = max(getattr(self, "_ready_at", 0.0), time.perf_counter()) + 0.55 * self.gpu_s
+
+    def act_done(self):
+        return time.perf_counter() >= getattr(self, "_ready_at", 0.0)
+
+    def wait(self):
+        while time.perf_counter() < getattr(self, "_ready_at", 0.0):
             pass
         self.step_np.action[:] = self.rng.integers(0, A, len(self.step_np.action))
 
