@@ -127,3 +127,51 @@ def test_loss_fails_loudly_without_cuda():
     with pytest.raises(_lib.B200LibraryError):
         loss_ops.dqn_loss(q, torch.zeros(4, 3), None, torch.zeros(4, dtype=torch.long), torch.zeros(4),
                           torch.zeros(4, dtype=torch.bool), None, 0.99, 1.0)
+
+
+def test_grad_destination_claims_a_slot_once_per_zero_grad():
+    """algos/optim.py ``grad_destination`` (host logic, CPU tensors): a parameter's slot of the flat gradient buffer is
+    handed out once per ``zero_grad`` and only while ``.grad`` is empty; everything else gets a fresh tensor that autograd
+    accumulates as usual; and autograd adopts the slot view without copying."""
+    import torch
+    from rlpyt_b200.algos.optim import grad_destination
+
+    class Owner:
+        _stamp, direct_grads = 1, True
+    flat = torch.zeros(12)
+    p = torch.nn.Parameter(torch.randn(2, 3))
+    p._flat_grad = dict(owner=Owner, slot=flat[4:10], stamp=-1)
+    p.grad = None
+    a = grad_destination(p)
+    assert a.data_ptr() == flat[4:10].data_ptr() and a.shape == p.shape
+    b = grad_destination(p)                                   # second use in the same backward: accumulate the usual way
+    assert b.data_ptr() != a.data_ptr() and b.shape == p.shape
+    Owner._stamp = 2                                          # zero_grad
+    p.grad = torch.zeros(2, 3)                                # ... but a gradient has already arrived from elsewhere
+    assert grad_destination(p).data_ptr() != flat[4:10].data_ptr()
+    p.grad = None
+    Owner.direct_grads = False
+    assert grad_destination(p).data_ptr() != flat[4:10].data_ptr()
+    Owner.direct_grads = True
+    assert grad_destination(p).data_ptr() == flat[4:10].data_ptr()
+    q = torch.nn.Parameter(torch.randn(3))                    # a parameter no FlatAdam manages
+    assert grad_destination(q).shape == q.shape
+
+    class Mul(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.w = w
+            ctx.save_for_backward(x)
+            return x * w
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,) = ctx.saved_tensors
+            dest = grad_destination(ctx.w)
+            torch.mul(g, x, out=dest)
+            return g * ctx.w, dest
+    Owner._stamp = 3
+    p.grad = None
+    x = torch.randn(2, 3)
+    Mul.apply(x, p).sum().backward()
+    assert p.grad.data_ptr() == flat[4:10].data_ptr() and torch.equal(flat[4:10].view(2, 3), x)   # adopted, not copied
